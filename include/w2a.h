@@ -1,0 +1,139 @@
+/*
+ * w2a.h -- C ABI of the B200-native HeatAlertEnv reset/step hot path.
+ *
+ * The reference (NSAPH-Projects/weather2alert) has no FFI of its own: the path sits
+ * behind a Gymnasium `Env` written in Python.  Every entry point below therefore cites
+ * the Python method it replaces (paths relative to the reference checkout); the Python
+ * classes in `weather2alert_b200/` bind these symbols with ctypes and mirror the
+ * reference's signatures, and INTEGRATION.md shows the stub a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative W2A_E_* code; the message for
+ *     the last failure on a context is returned by w2a_last_error();
+ *   - the caller owns every buffer; the library never allocates outputs nor frees
+ *     inputs (the *_host entry points own only their private staging buffers);
+ *   - "dev" pointers are device pointers on the context's GPU; kernels are enqueued on
+ *     the caller-supplied `stream` (a cudaStream_t passed as void*, NULL = default
+ *     stream) and the call returns without synchronising;
+ *   - a context is not thread-safe; no C++ exception crosses this boundary.
+ */
+#ifndef W2A_H_
+#define W2A_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W2A_VERSION 100 /* 0.1.0 */
+
+#define W2A_OK 0
+#define W2A_E_INVALID (-1)  /* bad argument (null pointer, size, dtype, variant) */
+#define W2A_E_CUDA (-2)     /* CUDA runtime error; text in w2a_last_error */
+#define W2A_E_NOTREADY (-3) /* tables / host env set not installed yet */
+#define W2A_E_NOMEM (-4)
+
+/* Observation layout: 29 float32 slots per env, row-major [n, 29]; slot order is
+ * `info["feature_names"]` of the reference (src/weather2alert/env.py:182-183). */
+#define W2A_OBS_DIM 29
+/* Device table row strides (see DESIGN.md "Data layout in HBM"). */
+#define W2A_XREW_STRIDE 24 /* float64 per day-row: reward features read from the table */
+#define W2A_XOBS_STRIDE 32 /* float32 per day-row: observation slots, lane-permuted */
+#define W2A_COEF_STRIDE 64 /* float32 per (county, posterior sample): 2 heads x 28, lane-permuted */
+
+/* action_dtype */
+#define W2A_ACT_U8 0
+#define W2A_ACT_I32 1
+#define W2A_ACT_I64 2
+
+/* kernel variant for w2a_step */
+#define W2A_STEP_AUTO 0
+#define W2A_STEP_THREAD 1 /* one thread per env (small batches, reference kernel) */
+#define W2A_STEP_COOP 2   /* 8 lanes per env, coalesced gathers + warp-shuffle reduction */
+
+/* per-env budget value meaning "use the episode's historical budget"
+ * (env.py:167-170: `self.ep["remaining_budget"].iloc[0]`). */
+#define W2A_BUDGET_DEFAULT INT32_MIN
+
+typedef struct w2a_ctx w2a_ctx;
+
+int w2a_version(void);
+/* Message of the last failure on `ctx` (or of the last failed w2a_create when ctx is
+ * NULL).  Never NULL. */
+const char* w2a_last_error(const w2a_ctx* ctx);
+
+/* One context per device.  Replaces the table-holding half of
+ * HeatAlertEnv.__init__ (env.py:20-105). */
+int w2a_create(int device, w2a_ctx** out);
+int w2a_destroy(w2a_ctx* ctx);
+
+/* Install the HBM-resident feature store (replaces `self.merged`, env.py:49-56).
+ *   xrew    dev float64 [S*Y*T, 24]  table-sourced reward features, slots 0..22 and 26
+ *   xobs    dev float32 [S*Y*T, 32]  observation slots, float at 4*q+i holds slot 8*i+q
+ *   n_days  dev uint8   [S*Y]        days in episode (county, year); 0 = no such episode
+ *   budget0 dev int32   [S*Y]        historical `remaining_budget` of day 0 (env.py:169)
+ * The tables are referenced, not copied, and must outlive their use.  S*Y*T < 2^24. */
+int w2a_set_features(w2a_ctx* ctx, const double* xrew, const float* xobs,
+                     const uint8_t* n_days, const int32_t* budget0, int S, int Y, int T);
+
+/* Install the posterior coefficient draws (replaces `self.baseline_coefs` /
+ * `self.effectiveness_coefs`, env.py:77-82).
+ *   w  dev float32 [S_w*P, 64]; vector (col*P + p) holds the 2x28 coefficients of county
+ *      column `col`, posterior sample `p`, in the lane-permuted order of DESIGN.md. */
+int w2a_set_coefs(w2a_ctx* ctx, const float* w, int P, int S_w);
+
+/* Bytes of the opaque per-env state for `n` envs (16 bytes per env, two SoA planes). */
+size_t w2a_state_bytes(int64_t n);
+
+/* Reset `n` envs from host-sampled index streams (replaces HeatAlertEnv.reset +
+ * _get_episode, env.py:107-184, after the RNG draws).  All arrays are dev, length n.
+ *   loc       county index into the feature store (episode weather; quirk Q7)
+ *   year      year index into the feature store
+ *   coef_col  column into the coefficient tensors: fips_list index, or the index inside
+ *             the similar-county list when augmenting (env.py:117,199; quirk Q6)
+ *   coef_idx  posterior sample (env.py:160)
+ *   budget    alert budget, W2A_BUDGET_DEFAULT per env (or NULL for all) = historical
+ *   mask      NULL, or uint8 per env: only envs with mask != 0 are reset
+ * Writes state, the first observation and (if non-NULL) remaining[]. */
+int w2a_reset(w2a_ctx* ctx, void* stream, int64_t n, const int32_t* loc,
+              const int32_t* year, const int32_t* coef_col, const int32_t* coef_idx,
+              const int32_t* budget, const uint8_t* mask, void* state, float* obs,
+              int32_t* remaining);
+
+/* One env.step for `n` envs in one launch (replaces HeatAlertEnv.step + _get_reward +
+ * _get_obs + _get_info, env.py:186-262).
+ *   action      dev [n], dtype per action_dtype; non-zero = issue an alert
+ *   state       in/out
+ *   obs         in/out dev float32 [n,29]: rows of envs that are already on their last
+ *               day are left untouched, exactly as the reference returns the previous
+ *               observation object on and after the terminal step (env.py:257-262)
+ *   reward      out dev float32 [n]
+ *   terminated  out dev uint8 [n]
+ *   remaining   out dev int32 [n] or NULL  (info["remaining_budget"], post-action)
+ *   at_budget   out dev uint8 [n] or NULL  (info["at_budget"], pre-action) */
+int w2a_step(w2a_ctx* ctx, void* stream, int64_t n, const void* action, int action_dtype,
+             void* state, float* obs, float* reward, uint8_t* terminated,
+             int32_t* remaining, uint8_t* at_budget, int variant);
+
+/* ---- host-buffer entry points: the call a CPU-side RL loop makes ------------------
+ * The context owns a device-resident env set; every call copies its inputs from and its
+ * outputs to HOST memory (pinned for full PCIe speed), pipelined in chunks over several
+ * streams, and returns after the outputs have landed. */
+int w2a_host_envs_create(w2a_ctx* ctx, int64_t n);
+int w2a_host_envs_destroy(w2a_ctx* ctx);
+int w2a_reset_host(w2a_ctx* ctx, const int32_t* loc, const int32_t* year,
+                   const int32_t* coef_col, const int32_t* coef_idx,
+                   const int32_t* budget, const uint8_t* mask, float* obs,
+                   int32_t* remaining);
+int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward,
+                  uint8_t* terminated, int32_t* remaining, uint8_t* at_budget);
+/* Number of kernels this context has launched (bench.py's `gpu_launches`). */
+int64_t w2a_launch_count(const w2a_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2A_H_ */
