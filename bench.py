@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the HeatAlertEnv step hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3_1m] [--impl ours|reference]
+
+One "step" is one `env.step` over every env of the batch (all GPUs); the timed region is
+EXACTLY K steps after W warm-up steps, CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.  Rank 0 prints ONE JSON line.
+
+Workloads (BASELINE.json `configs`; DESIGN.md "Measurement" says why cfg3_1m is the default):
+  cfg2_4096  4 096 envs/GPU, env i -> county i mod S            (configs[1]; launch-latency bound)
+  cfg3_1m    2**20 envs/GPU, env i -> county i mod S            (configs[2] size; default)
+  cfg4_2m    2**21 envs/GPU, similar_climate_counties=True      (configs[3] = 16M envs / 8 GPUs)
+  cfg5_8m    2**23 envs/GPU                                     (configs[4] = 64M envs / 8 GPUs)
+All use the linear-format checkpoint layout (S=746 counties, P=100 draws; `nn_*`
+checkpoints have the identical layout and take the same path), 11
+years x 153 days of synthetic weather, uniform random actions (p=0.5) resident in HBM.
+
+`--impl reference` times the reference's own CPU implementation on the host cores: the
+UNMODIFIED reference env from baseline/_ref (one forked worker per core) when that
+install is present, else the C port in oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+S_COUNTIES, N_YEARS, P_SAMPLES = 746, 11, 100
+WORKLOADS = {
+    "cfg2_4096": dict(envs_per_gpu=4096, augment=False, desc="BASELINE configs[1]: 4096 envs, env i -> county i mod S"),
+    "cfg3_1m": dict(envs_per_gpu=1 << 20, augment=False, desc="BASELINE configs[2] size: 2^20 envs/GPU, env i -> county i mod S"),
+    "cfg4_2m": dict(envs_per_gpu=1 << 21, augment=True, desc="BASELINE configs[3]: 2^21 envs/GPU (16M on 8), similar_climate_counties"),
+    "cfg5_8m": dict(envs_per_gpu=1 << 23, augment=False, desc="BASELINE configs[4]: 2^23 envs/GPU (64M on 8)"),
+}
+# Algorithmic bytes per env-step (DESIGN.md "Roofline"):
+#  streaming: what must cross HBM every step -- action 1 + state 16 read, state 8 + obs 116 +
+#             reward 4 + terminated 1 + remaining 4 + at_budget 1 written = 151
+#  canonical: SURVEY.md 8(d) = 466, which also counts the feature row (96) and the 56
+#             coefficients (224) that this design serves from L2 instead of HBM
+BYTES_STREAMING = 1 + 16 + 8 + 116 + 4 + 1 + 4 + 1
+BYTES_CANONICAL = 466
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_tables(years=N_YEARS, counties=S_COUNTIES, samples=P_SAMPLES):
+    from weather2alert_b200 import synthetic
+
+    fips, zones = synthetic.synthetic_counties(counties, seed=0)
+    store = synthetic.make_store(fips, list(range(2006, 2006 + years)), seed=1, zones=zones)
+    weights = synthetic.make_weights(fips, samples, seed=2)
+    return store, weights
+
+
+def index_streams(store, weights, n, rank, augment):
+    """env i -> county (global i) mod S; year / posterior sample / similar-list index drawn with
+    numpy's default_rng(1234 + rank)."""
+    from weather2alert_b200.sampling import EpisodeSampler
+
+    rng = np.random.default_rng(1234 + rank)
+    S = len(weights.fips_list)
+    list_idx = (np.arange(n, dtype=np.int64) + rank * n) % S
+    sp = EpisodeSampler(store, weights)
+    s = sp.draw_bulk(rng, n, list_idx, augment)
+    return s
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.stop_flag, self.ok = [], threading.Event(), False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as exc:  # pragma: no cover
+            log(f"clock sampling unavailable: {exc}")
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self, t0, t1):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost",
+                 0x100: "display_clock_setting"}
+        bits = 0
+        for _, _, r in inside:
+            bits |= r
+        reasons = [n for b, n in names.items() if bits & b]
+        return {"sm_mhz": statistics.median([s[1] for s in inside]) if inside else None,
+                "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(inside)}
+
+
+# =================================================================================================
+# our arm
+# =================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from weather2alert_b200 import _lib
+    from weather2alert_b200.core import HeatAlertCore
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = WORKLOADS[args.workload]
+    n = args.envs_per_gpu or wl["envs_per_gpu"]
+    K, W = args.steps, args.warmup
+    t_setup = time.time()
+    store, weights = make_tables()
+    core = HeatAlertCore(store, weights, dev)
+    s = index_streams(store, weights, n, rank, wl["augment"])
+    idx = {k: torch.from_numpy(v).to(dev) for k, v in s.items()}
+    T = int(store.n_days.max())
+    variant = {"auto": _lib.STEP_AUTO, "thread": _lib.STEP_THREAD, "coop": _lib.STEP_COOP}[args.variant]
+
+    state = core.alloc_state(n)
+    obs = torch.zeros((n, 29), dtype=torch.float32, device=dev)
+    reward = torch.zeros(n, dtype=torch.float32, device=dev)
+    term = torch.zeros(n, dtype=torch.uint8, device=dev)
+    rem = torch.zeros(n, dtype=torch.int32, device=dev)
+    atb = torch.zeros(n, dtype=torch.uint8, device=dev)
+    # uniform random actions, p = 0.5, one row per day of the summer, resident in HBM
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = (torch.rand((T, n), generator=g, device=dev) < 0.5).to(torch.uint8)
+    step = core.bind_step(state, obs, reward, term, rem, atb, variant=variant)
+
+    def do_reset():
+        core.reset(state, obs, idx["loc"], idx["year"], idx["coef_col"], idx["coef_idx"], remaining=rem)
+
+    log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s: {n} envs, tables "
+        f"{(core.xrew.numel() * 8 + core.xobs.numel() * 4 + core.w.numel() * 4) / 1e6:.0f} MB")
+
+    # ---- device-resident throughput: `value` ---------------------------------------------------
+    def run_steps(k, t):
+        """k steps starting at day t of the summer; a finished summer is reset in place (included)."""
+        for _ in range(k):
+            step(actions[t])
+            t += 1
+            if t == T:
+                do_reset()
+                t = 0
+        return t
+
+    do_reset()
+    t = run_steps(W, 0)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = core.launch_count
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    ev0.record()
+    t = run_steps(K, t)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    clocks.stop_flag.set()
+    launches = core.launch_count - launches0
+    ms = ev0.elapsed_time(ev1)
+    ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    value = n * world * K / (ms_max * 1e-3)
+
+    # optional return-statistics reduction (the only collective of the path)
+    stats = torch.stack([reward.double().sum(), (reward.double() ** 2).sum(),
+                         torch.tensor(float(n), dtype=torch.float64, device=dev), rem.double().sum()])
+    if world > 1:
+        dist.all_reduce(stats)
+
+    # ---- end to end through the host-buffer C entry points: `e2e` ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        core.host_envs_create(n)
+        pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()  # noqa: E731
+        h_obs, h_rew, h_term = pin((n, 29), torch.float32), pin(n, torch.float32), pin(n, torch.uint8)
+        h_rem, h_atb = pin(n, torch.int32), pin(n, torch.uint8)
+        h_act = (torch.rand((8, n)) < 0.5).to(torch.uint8).pin_memory()
+        core.reset_host(s["loc"], s["year"], s["coef_col"], s["coef_idx"], h_obs, remaining=h_rem)
+        ke = max(3, min(K, args.e2e_steps))
+        for i in range(3):
+            core.step_host(h_act[i % 8], h_obs, h_rew, h_term, h_rem, h_atb)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0 = time.perf_counter()
+        for i in range(ke):
+            core.step_host(h_act[i % 8], h_obs, h_rew, h_term, h_rem, h_atb)
+        torch.cuda.synchronize()
+        e_s = time.perf_counter() - e0
+        e_t = torch.tensor([e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world * ke / float(e_t.item()), "unit": UNIT, "steps": ke,
+               "h2d_bytes_per_step": n * world * 1,
+               "d2h_bytes_per_step": n * world * (29 * 4 + 4 + 1 + 4 + 1),
+               "api": "w2a_step_host (C ABI, pinned host buffers, 3-stream chunked pipeline)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    sec_per_step = ms_max * 1e-3 / K
+    ach = BYTES_STREAMING * n / sec_per_step / 1e9
+    ach_c = BYTES_CANONICAL * n / sec_per_step / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "envs_per_gpu": n, "envs_total": n * world,
+                   "counties": S_COUNTIES, "years": N_YEARS, "days": T, "posterior_samples": P_SAMPLES,
+                   "weights": "linear-format synthetic (nn_* checkpoints share the layout and the path)",
+                   "augment": wl["augment"], "mode": "per-step launches", "variant": args.variant,
+                   "parallelism": f"env-sharded x{world}, no step-time collective",
+                   "l2": "per-step streaming traffic (151 B x envs) exceeds the 126 MB L2 for >= 2^20 envs; "
+                         "tables (feature rows of the day + coefficients) are meant to stay L2-resident"},
+        "gpu_launches": int(launches),
+        "wall_s": w1 - w0,
+        "clocks": clocks.summary(w0, w1),
+        "e2e": e2e,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "bytes_per_env_step": BYTES_STREAMING, "peak_source": peak_src,
+                     "kernel": "step_coop_kernel" if (variant == _lib.STEP_COOP or (variant == 0 and n >= 32768)) else "step_thread_kernel",
+                     "note": "achieved = streaming bytes (HBM-mandatory) x envs / mean step time over the timed region"},
+        "roofline_canonical_466B": {"achieved": ach_c, "frac": ach_c / peak,
+                                    "note": "SURVEY 8(d) canonical 466 B/env-step; includes table gathers served from L2"},
+        "return_stats": {"sum_reward": float(stats[0]), "sum_reward_sq": float(stats[1]), "n": float(stats[2]),
+                         "sum_remaining": float(stats[3]), "reduced_over": world},
+    }
+    traffic_file = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as fh:
+                tr = json.load(fh)
+            if tr.get("workload") == args.workload and tr.get("envs") == n:
+                out["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_port(store, weights, args.cpu_seconds)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# =================================================================================================
+# CPU baselines
+# =================================================================================================
+def cpu_baseline_port(store, weights, budget_s=12.0):
+    """oracle/c/heat_oracle.c (the reference algorithm restated in C, OpenMP over envs) on the host
+    cores, on a bounded sample of the same workload."""
+    from oracle import c_oracle
+
+    if not c_oracle.available():
+        import __graft_entry__ as g
+
+        g.build_oracle()
+    n = 1 << 16
+    rng = np.random.default_rng(99)
+    S = len(weights.fips_list)
+    loc = (np.arange(n) % S).astype(np.int32)
+    co = c_oracle.COracle(store.feat, store.sig_code, store.n_days, weights.coef, n)
+    co.reset(loc, rng.integers(0, store.shape[1], n), loc, rng.integers(0, weights.n_samples, n))
+    acts = (rng.random((152, n)) < 0.5).astype(np.uint8)
+    for i in range(3):
+        co.step(acts[i])
+    t0, steps = time.perf_counter(), 0
+    while steps < 149 and time.perf_counter() - t0 < budget_s:
+        co.step(acts[3 + steps])
+        steps += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": UNIT, "cores": co.threads, "kind": "port",
+            "sample": f"{n} envs x {steps} steps of the same workload through oracle/c/heat_oracle.c (OpenMP)"}
+
+
+_REF_BASE_ENV = None  # built once in the parent; forked workers share its frames copy-on-write
+
+
+def _ref_worker(conn, seeds, locations):
+    """One forked worker: a few reference envs, stepped on command."""
+    import copy
+    import warnings
+
+    warnings.simplefilter("ignore")
+    envs = []
+    for sd, loc in zip(seeds, locations):
+        env = copy.copy(_REF_BASE_ENV)  # shares the (read-only) merged frame and coefficient tensors
+        env.reset(location=loc, seed=int(sd))
+        envs.append(env)
+    rng = np.random.default_rng(seeds[0])
+    conn.send("ready")
+    while True:
+        k = conn.recv()
+        if k is None:
+            break
+        for _ in range(k):
+            for env in envs:
+                _, _, done, _, _ = env.step(int(rng.integers(2)))
+                if done:
+                    env.reset(seed=int(rng.integers(10000)))
+        conn.send(k * len(envs))
+
+
+def run_reference(args):
+    """The reference's own CPU implementation on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import multiprocessing as mp
+    import tempfile
+
+    from oracle import ref_harness
+
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    K, W = args.steps, args.warmup
+    if ref_harness.reference_location() is None:
+        # no install of the reference travelled here: fall back to the C port of its algorithm
+        store, weights = make_tables()
+        cb = cpu_baseline_port(store, weights, 20.0)
+        out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+               "steps": K, "warmup": W, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"]},
+               "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out), flush=True)
+        return
+
+    from weather2alert_b200 import synthetic
+
+    # Same county list / checkpoint shape as our arm; 3 years of weather instead of 11 keeps
+    # the pandas frames of every forked worker small -- the reference's step cost does not
+    # depend on the table size (it works on one episode frame).
+    t0 = time.time()
+    fips, zones = synthetic.synthetic_counties(S_COUNTIES, seed=0)
+    store = synthetic.make_store(fips, [2006, 2007, 2008], seed=1, zones=zones)
+    weights = synthetic.make_weights(fips, P_SAMPLES, seed=2)
+    fixture = tempfile.mkdtemp(prefix="w2a_ref_fixture_")
+    synthetic.write_reference_files(store, weights, fixture)
+    log(f"reference fixture written in {time.time() - t0:.1f}s")
+    global _REF_BASE_ENV
+    _REF_BASE_ENV = ref_harness.make_reference_env(fixture)
+    n_workers = max(1, min(cores, args.ref_workers or cores))
+    envs_per_worker = 2
+    ctx = mp.get_context("fork")
+    workers = []
+    for w in range(n_workers):
+        parent, child = ctx.Pipe()
+        seeds = [1234 + w * envs_per_worker + j for j in range(envs_per_worker)]
+        locs = [fips[(w * envs_per_worker + j) % len(fips)] for j in range(envs_per_worker)]
+        p = ctx.Process(target=_ref_worker, args=(child, seeds, locs), daemon=True)
+        p.start()
+        workers.append((p, parent))
+    for _, c in workers:
+        assert c.recv() == "ready"
+    log(f"{n_workers} reference workers x {envs_per_worker} envs ready in {time.time() - t0:.1f}s")
+
+    def run(k):
+        for _, c in workers:
+            c.send(k)
+        return sum(c.recv() for _, c in workers)
+
+    run(max(1, W))
+    t0 = time.perf_counter()
+    total = run(K)
+    dt = time.perf_counter() - t0
+    for p, c in workers:
+        c.send(None)
+    value = total / dt
+    sample = (f"{n_workers} forked workers x {envs_per_worker} unmodified reference envs (baseline/_ref, gymnasium stub, "
+              f"local fixture {S_COUNTIES} counties x 3 years), {K} steps each, random actions")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+           "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": args.workload, "desc": wl["desc"], "envs_total": n_workers * envs_per_worker},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_workers, "kind": "reference", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3060)
+    ap.add_argument("--warmup", type=int, default=153)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=list(WORKLOADS), default="cfg3_1m")
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
+    ap.add_argument("--variant", choices=["auto", "thread", "coop"], default="auto")
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-workers", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.steps > 200:
+            args.steps = 200  # 3 ms per reference env-step: keep the arm to a couple of minutes
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,261 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden trajectories and
+with the oracle.  Bar (BASELINE.json north_star): observations, counters and flags
+bit-exact; rewards within 1e-5 relative in fp32."""
+import numpy as np
+import pytest
+
+from conftest import assert_obs_equal
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+REWARD_RTOL = 1e-5   # north_star tolerance
+REWARD_ATOL = 1e-10  # rewards that underflow towards 0 (sigmoid saturated) have no relative meaning
+VARIANTS = {"thread": 1, "coop": 2}
+
+
+@pytest.fixture(scope="module")
+def cores(golden):
+    from weather2alert_b200.core import HeatAlertCore
+
+    store = golden.store()
+    return {name: HeatAlertCore(store, golden.weights(name), "cuda:0") for name in ("std", "large")}
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def _golden_batch(golden, wname):
+    eps = [ep for sc, ep in golden.all_episodes() if sc["weights"] == wname]
+    idx = dict(
+        loc=np.array([golden.fips.index(ep["episode_index"].split("_")[0]) for ep in eps], np.int32),
+        year=np.array([golden.years.index(int(ep["episode_index"].split("_")[1])) for ep in eps], np.int32),
+        coef_col=np.array([ep["location_index"] for ep in eps], np.int32),
+        coef_idx=np.array([ep["coef_index"] for ep in eps], np.int32),
+        budget=np.array([ep["budget"] for ep in eps], np.int32),
+    )
+    return eps, idx, [golden.episode(ep["key"]) for ep in eps]
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("wname", ["std", "large"])
+def test_reference_trajectories_as_one_batch(golden, cores, wname, variant):
+    """Every episode the unmodified reference produced, replayed in one batch per step."""
+    core = cores[wname]
+    eps, idx, refs = _golden_batch(golden, wname)
+    n = len(eps)
+    state = core.alloc_state(n)
+    obs = torch.full((n, 29), -7.0, device="cuda")
+    rem = torch.zeros(n, dtype=torch.int32, device="cuda")
+    core.reset(state, obs, *(_dev(idx[k]) for k in ("loc", "year", "coef_col", "coef_idx")),
+               budget=_dev(idx["budget"]), remaining=rem)
+    assert_obs_equal(obs.cpu().numpy(), np.stack([r["obs0"] for r in refs]), "reset obs")
+    np.testing.assert_array_equal(rem.cpu().numpy(), idx["budget"])
+    reward = torch.zeros(n, device="cuda")
+    term = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    atb = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    horizon = max(len(r["actions"]) for r in refs)
+    worst = 0.0
+    for i in range(horizon):
+        live = np.array([i < len(r["actions"]) for r in refs])
+        act = np.array([r["actions"][i] if i < len(r["actions"]) else 0 for r in refs], np.uint8)
+        core.step(state, _dev(act), obs, reward, term, rem, atb, variant=VARIANTS[variant])
+        o, rw, tm, rm, ab = (x.cpu().numpy() for x in (obs, reward, term, rem, atb))
+        want_obs = np.stack([r["obs"][min(i, len(r["actions"]) - 1)] for r in refs])
+        assert_obs_equal(o[live], want_obs[live], f"obs step {i}")
+        want_r = np.array([r["reward"][i] if i < len(r["actions"]) else 0.0 for r in refs])
+        np.testing.assert_allclose(rw[live], want_r[live], rtol=REWARD_RTOL, atol=REWARD_ATOL, err_msg=f"step {i}")
+        worst = max(worst, float(np.max(np.abs(rw[live] - want_r[live]) / np.maximum(np.abs(want_r[live]), 1e-30))))
+        np.testing.assert_array_equal(tm[live].astype(bool), np.array([r["done"][i] for r in refs if i < len(r["actions"])]))
+        np.testing.assert_array_equal(rm[live], np.array([r["rem"][i] for r in refs if i < len(r["actions"])]))
+        np.testing.assert_array_equal(ab[live].astype(bool), np.array([r["atb"][i] for r in refs if i < len(r["actions"])]))
+    assert worst < REWARD_RTOL
+
+
+def test_single_env_facade_replays_every_reference_scenario(golden):
+    """`HeatAlertEnv` with the reference's own call sequence: ctor kwargs, reset kwargs
+    (seeded RNG draws, sticky budgets, budget sampling), step, info dict."""
+    from weather2alert_b200 import HeatAlertEnv
+
+    store = golden.store()
+    for sc in golden.meta:
+        env = HeatAlertEnv(weights=golden.weights(sc["weights"]), store=store, device="cuda:0", **sc["ctor"])
+        for ep in sc["episodes"]:
+            ref = golden.episode(ep["key"])
+            obs, info = env.reset(**ep["reset"])
+            where = f"{sc['name']} {ep['key']}"
+            assert obs.dtype == np.float32 and obs.shape == (29,)
+            assert_obs_equal(obs, ref["obs0"], where)
+            assert info["episode_index"] == ep["episode_index"] and str(info["location"]) == ep["location"]
+            assert info["location_index"] == ep["location_index"]
+            assert info["remaining_budget"] == ep["remaining_budget0"] and info["at_budget"] is False
+            assert info["feature_names"] == ep["feature_names"]
+            assert env.coef_index == ep["coef_index"] and env.budget == ep["budget"] and env.n_days == ep["n_days"]
+            for i, a in enumerate(ref["actions"]):
+                obs, r, done, trunc, info = env.step(int(a))
+                assert_obs_equal(obs, ref["obs"][i], f"{where} step {i}")
+                assert isinstance(r, float) and r == pytest.approx(ref["reward"][i], rel=REWARD_RTOL, abs=REWARD_ATOL)
+                assert done is bool(ref["done"][i]) and trunc is False
+                assert info["remaining_budget"] == ref["rem"][i] and info["at_budget"] is bool(ref["atb"][i])
+            assert env.t == min(len(ref["actions"]), ep["n_days"] - 1)
+
+
+def test_single_env_errors(golden):
+    from weather2alert_b200 import HeatAlertEnv
+
+    env = HeatAlertEnv(weights=golden.weights("std"), store=golden.store(), seed=1234)
+    obs, info = env.reset(location="06037")  # ctor seed used (README form)
+    assert info["episode_index"] == golden.meta[0]["episodes"][0]["episode_index"]
+    with pytest.raises(ValueError):
+        env.reset(location="99999")
+    with pytest.raises(KeyError):
+        HeatAlertEnv(weights=golden.weights("std"), store=golden.store(), years=[1999]).reset(location="06037")
+    assert env.action_space.n == 2 and env.observation_space.shape == (29,)
+
+
+def _random_case(seed, n, n_counties=40, n_years=3, p_samples=20, augment=False, short=True):
+    from weather2alert_b200 import synthetic
+
+    rng = np.random.default_rng(seed)
+    fips, zones = synthetic.synthetic_counties(n_counties, seed=seed)
+    n_days = np.full((n_counties, n_years), 153, np.uint8)
+    if short:
+        n_days[rng.integers(0, n_counties, 5), rng.integers(0, n_years, 5)] = rng.integers(1, 150, 5)
+    store = synthetic.make_store(fips, list(range(2006, 2006 + n_years)), seed=seed + 1, zones=zones, n_days=n_days,
+                                 p_alert=0.08)
+    weights = synthetic.make_weights(fips, p_samples, seed=seed + 2)
+    idx = dict(loc=rng.integers(0, n_counties, n), year=rng.integers(0, n_years, n),
+               coef_col=rng.integers(0, n_counties, n) if augment else None,
+               coef_idx=rng.integers(0, p_samples, n))
+    if idx["coef_col"] is None:
+        idx["coef_col"] = idx["loc"].copy()
+    budget = rng.integers(-1, 12, n)
+    budget[rng.random(n) < 0.3] = -(2**31)  # historical default
+    idx["budget"] = budget
+    return store, weights, {k: v.astype(np.int32) for k, v in idx.items()}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("n,augment", [(1, False), (33, True), (4096, False), (20011, True)])
+def test_random_batches_against_the_oracle(n, augment, variant):
+    """Seeded random batches (ragged sizes, short summers, budgets incl. 0/-1/default,
+    steps past the end) against oracle/heat_alert_oracle.batch_step."""
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200.core import HeatAlertCore
+
+    store, weights, idx = _random_case(1000 + n, n, augment=augment)
+    core = HeatAlertCore(store, weights, "cuda:0")
+    state = core.alloc_state(n)
+    obs = torch.zeros((n, 29), device="cuda")
+    rem = torch.zeros(n, dtype=torch.int32, device="cuda")
+    core.reset(state, obs, *(_dev(idx[k]) for k in ("loc", "year", "coef_col", "coef_idx")),
+               budget=_dev(idx["budget"]), remaining=rem)
+    st, o_ref = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"], idx["coef_col"],
+                                idx["coef_idx"], idx["budget"])
+    assert_obs_equal(obs.cpu().numpy(), o_ref)
+    np.testing.assert_array_equal(rem.cpu().numpy(), st["budget"])
+    reward = torch.zeros(n, device="cuda")
+    term = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    atb = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    rng = np.random.default_rng(5)
+    steps = 170 if n <= 4096 else 60
+    for i in range(steps):
+        p = (0.05, 0.5, 0.95)[i % 3]
+        act = (rng.random(n) < p).astype(np.int64)
+        core.step(state, _dev(act), obs, reward, term, rem, atb, variant=VARIANTS[variant])
+        o_ref, r_ref, d_ref, rem_ref, atb_ref = orc.batch_step(store.feat, store.sig_code, weights.coef, st, act)
+        assert_obs_equal(obs.cpu().numpy(), o_ref, f"step {i}")
+        np.testing.assert_allclose(reward.cpu().numpy(), r_ref, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+        np.testing.assert_array_equal(term.cpu().numpy().astype(bool), d_ref)
+        np.testing.assert_array_equal(rem.cpu().numpy(), rem_ref)
+        np.testing.assert_array_equal(atb.cpu().numpy().astype(bool), atb_ref)
+
+
+def test_action_dtypes_masked_reset_and_null_outputs():
+    from weather2alert_b200.core import HeatAlertCore
+
+    n = 777
+    store, weights, idx = _random_case(77, n)
+    core = HeatAlertCore(store, weights, "cuda:0")
+    d = {k: _dev(v) for k, v in idx.items()}
+    act = (np.random.default_rng(0).random((6, n)) < 0.5)
+    outs = {}
+    for dt in (torch.uint8, torch.int32, torch.int64, torch.bool):
+        state = core.alloc_state(n)
+        obs = torch.zeros((n, 29), device="cuda")
+        core.reset(state, obs, d["loc"], d["year"], d["coef_col"], d["coef_idx"], budget=d["budget"])
+        reward = torch.zeros(n, device="cuda")
+        term = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        for i in range(6):
+            core.step(state, torch.from_numpy(act[i]).cuda().to(dt), obs, reward, term)  # remaining/at_budget NULL
+        outs[dt] = (obs.clone(), reward.clone(), state.clone())
+    for dt in (torch.int32, torch.int64, torch.bool):
+        for a, b in zip(outs[torch.uint8], outs[dt]):
+            assert torch.equal(a.view(torch.uint8), b.view(torch.uint8))
+    # masked reset touches only the selected envs
+    obs0, _, state0 = outs[torch.uint8]
+    state, obs = state0.clone(), obs0.clone()
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[::3] = 1
+    core.reset(state, obs, d["loc"], d["year"], d["coef_col"], d["coef_idx"], budget=d["budget"], mask=mask)
+    keep = (mask == 0)
+    assert torch.equal(obs[keep].view(torch.int32), obs0[keep].view(torch.int32))
+    fresh_state = core.alloc_state(n)
+    fresh_obs = torch.zeros((n, 29), device="cuda")
+    core.reset(fresh_state, fresh_obs, d["loc"], d["year"], d["coef_col"], d["coef_idx"], budget=d["budget"])
+    sel = mask.bool()
+    assert torch.equal(obs[sel].view(torch.int32), fresh_obs[sel].view(torch.int32))
+    s_new, s_old, s_fresh = (x.view(2, n, 8) for x in (state, state0, fresh_state))
+    assert torch.equal(s_new[:, keep], s_old[:, keep]) and torch.equal(s_new[:, sel], s_fresh[:, sel])
+
+
+def test_host_buffer_entry_points_equal_device_path():
+    from weather2alert_b200.core import HeatAlertCore
+
+    n = 150_000  # three pipelined chunks
+    store, weights, idx = _random_case(99, n, short=False)
+    core = HeatAlertCore(store, weights, "cuda:0")
+    core.host_envs_create(n)
+    obs_h = np.zeros((n, 29), np.float32)
+    rem_h = np.zeros(n, np.int32)
+    core.reset_host(idx["loc"], idx["year"], idx["coef_col"], idx["coef_idx"], obs_h, budget=idx["budget"], remaining=rem_h)
+    state = core.alloc_state(n)
+    obs = torch.zeros((n, 29), device="cuda")
+    d = {k: _dev(v) for k, v in idx.items()}
+    core.reset(state, obs, d["loc"], d["year"], d["coef_col"], d["coef_idx"], budget=d["budget"])
+    np.testing.assert_array_equal(obs_h.view(np.int32), obs.cpu().numpy().view(np.int32))
+    reward = torch.zeros(n, device="cuda")
+    term = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    rem = torch.zeros(n, dtype=torch.int32, device="cuda")
+    atb = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    rew_h, term_h, atb_h = np.zeros(n, np.float32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        act = (rng.random(n) < 0.5).astype(np.uint8)
+        core.step_host(act, obs_h, rew_h, term_h, rem_h, atb_h)
+        core.step(state, _dev(act), obs, reward, term, rem, atb, variant=2)
+        np.testing.assert_array_equal(obs_h.view(np.int32), obs.cpu().numpy().view(np.int32))
+        np.testing.assert_array_equal(rew_h.view(np.int32), reward.cpu().numpy().view(np.int32))
+        np.testing.assert_array_equal(term_h, term.cpu().numpy())
+        np.testing.assert_array_equal(rem_h, rem.cpu().numpy())
+        np.testing.assert_array_equal(atb_h, atb.cpu().numpy())
+
+
+def test_abi_error_paths():
+    import ctypes as C
+
+    from weather2alert_b200 import _lib
+
+    lib = _lib.lib()
+    ctx = C.c_void_p()
+    assert lib.w2a_create(9999, C.byref(ctx)) == -1 and b"not in" in lib.w2a_last_error(None)
+    assert lib.w2a_create(0, C.byref(ctx)) == 0
+    assert lib.w2a_step(ctx, None, 8, None, 0, None, None, None, None, None, None, 0) == -3  # tables missing
+    assert b"w2a_set_features" in lib.w2a_last_error(ctx)
+    assert lib.w2a_step_host(ctx, None, None, None, None, None, None) == -3
+    assert lib.w2a_set_coefs(ctx, None, 1, 1) == -1
+    assert lib.w2a_destroy(ctx) == 0

@@ -1,0 +1,123 @@
+"""Vector env behaviour and size-independent properties at BASELINE.json sizes."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big_core():
+    """746 counties x 11 years, P=100: the shape of BASELINE.json configs[1..3]."""
+    from weather2alert_b200 import synthetic
+    from weather2alert_b200.core import HeatAlertCore
+
+    fips, zones = synthetic.synthetic_counties(746, seed=0)
+    store = synthetic.make_store(fips, list(range(2006, 2017)), seed=1, zones=zones)
+    weights = synthetic.make_weights(fips, 100, seed=2)
+    return HeatAlertCore(store, weights, "cuda:0")
+
+
+def test_vector_env_autoreset_and_oracle(golden):
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200 import HeatAlertVectorEnv
+
+    store, weights = golden.store(), golden.weights("std")
+    n = 300
+    env = HeatAlertVectorEnv(n, weights=weights, store=store, seed=11, similar_climate_counties=True)
+    obs, info = env.reset()
+    assert obs.shape == (n, 29) and obs.is_cuda and obs.dtype == torch.float32
+    idx = {k: v.cpu().numpy() for k, v in env._idx.items()}
+    st, o_ref = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"], idx["coef_col"],
+                                idx["coef_idx"], idx.get("budget"))
+    np.testing.assert_array_equal(obs.cpu().numpy(), o_ref.astype(np.float32))
+    rng = np.random.default_rng(1)
+    n_resets = 0
+    for i in range(320):
+        act = torch.from_numpy((rng.random(n) < 0.4)).cuda()
+        obs, rew, term, trunc, info = env.step(act)
+        assert term.dtype == torch.bool and not trunc.any()
+        o_ref, r_ref, d_ref, rem_ref, atb_ref = orc.batch_step(store.feat, store.sig_code, weights.coef, st, act.cpu().numpy())
+        np.testing.assert_array_equal(term.cpu().numpy(), d_ref)
+        np.testing.assert_allclose(rew.cpu().numpy(), r_ref, rtol=1e-5, atol=1e-10)
+        done = d_ref
+        if done.any():  # SAME_STEP autoreset: those envs now show the first obs of a new episode
+            n_resets += int(done.sum())
+            idx = {k: v.cpu().numpy() for k, v in env._idx.items()}
+            st2, o2 = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"],
+                                      idx["coef_col"], idx["coef_idx"], idx.get("budget"))
+            for k in ("loc", "year", "col", "p", "budget", "t", "streak", "n_days", "obs"):
+                st[k] = np.where(done.reshape((-1,) + (1,) * (st[k].ndim - 1)), st2[k], st[k])
+            st["hist"][done] = 0
+            o_ref = st["obs"]
+        np.testing.assert_array_equal(obs.cpu().numpy()[~done], o_ref[~done].astype(np.float32))
+        np.testing.assert_array_equal(obs.cpu().numpy()[done], st["obs"][done].astype(np.float32))
+    assert n_resets >= 2 * n  # every env finished at least two summers (one of them is 150 days long)
+
+
+def test_vector_env_state_dict_replay(golden):
+    from weather2alert_b200 import HeatAlertVectorEnv
+
+    env = HeatAlertVectorEnv(64, weights=golden.weights("std"), store=golden.store(), seed=5)
+    env.reset()
+    acts = [torch.from_numpy(np.random.default_rng(i).random(64) < 0.5).cuda() for i in range(30)]
+    for a in acts[:10]:
+        env.step(a)
+    snap = env.state_dict()
+    first = [tuple(x.clone() for x in env.step(a)[:3]) for a in acts[10:]]
+    env.load_state_dict(snap)
+    again = [tuple(x.clone() for x in env.step(a)[:3]) for a in acts[10:]]
+    for f, g in zip(first, again):
+        for x, y in zip(f, g):
+            assert torch.equal(x.view(torch.uint8), y.view(torch.uint8))
+
+
+def test_million_envs_properties(big_core):
+    """BASELINE configs[2] size (2**20 envs): the two step variants agree, the launch is
+    deterministic, halves equal the whole (sharding), and the budget invariants hold."""
+    core = big_core
+    n = 1 << 20
+    rng = np.random.default_rng(42)
+    S, Y, P = core.S, core.Y, core.P
+    mk = lambda a: torch.from_numpy(a.astype(np.int32)).cuda()  # noqa: E731
+    loc = mk(np.arange(n) % S)
+    year, cidx = mk(rng.integers(0, Y, n)), mk(rng.integers(0, P, n))
+    budget = mk(rng.integers(0, 10, n))
+
+    def run(variant, lo, hi, steps=20):
+        m = hi - lo
+        state = core.alloc_state(m)
+        obs = torch.zeros((m, 29), device="cuda")
+        core.reset(state, obs, loc[lo:hi].contiguous(), year[lo:hi].contiguous(), loc[lo:hi].contiguous(),
+                   cidx[lo:hi].contiguous(), budget=budget[lo:hi].contiguous())
+        reward = torch.zeros(m, device="cuda")
+        term = torch.zeros(m, dtype=torch.uint8, device="cuda")
+        rem = torch.zeros(m, dtype=torch.int32, device="cuda")
+        atb = torch.zeros(m, dtype=torch.uint8, device="cuda")
+        issued = torch.zeros(m, dtype=torch.int32, device="cuda")
+        ret = torch.zeros(m, dtype=torch.float64, device="cuda")
+        g = torch.Generator(device="cuda").manual_seed(7)
+        for _ in range(steps):
+            act = (torch.rand(n, device="cuda", generator=g) < 0.5)[lo:hi].to(torch.uint8)
+            prev = rem.clone() if _ else budget[lo:hi].clone()
+            core.step(state, act, obs, reward, term, rem, atb, variant=variant)
+            issued += prev - rem
+            ret += reward.double()
+            assert int(rem.min()) >= 0                               # never over budget
+            assert bool(((prev - rem == 1) | (prev - rem == 0)).all())
+            assert bool((atb.bool() == (prev == 0)).all())           # at_budget is the pre-action flag
+            assert bool((obs[:, 25] == rem.float()).all()) and bool((obs[:, 28] <= 14).all())
+            assert bool((reward <= 0).all()) and bool(torch.isfinite(reward).all()) and not term.any()
+        assert bool((issued <= budget[lo:hi]).all())
+        return obs, ret, rem, state
+
+    o1, r1, m1, s1 = run(1, 0, n)
+    o2, r2, m2, s2 = run(2, 0, n)
+    assert torch.equal(o1, o2) and torch.equal(m1, m2) and torch.equal(s1, s2)
+    assert torch.allclose(r1, r2, rtol=1e-6, atol=1e-9)  # float64 sums of float32 rewards; only summation order differs
+    o3, r3, m3, s3 = run(2, 0, n)
+    assert torch.equal(r2, r3) and torch.equal(o2, o3)        # deterministic
+    half = n // 2
+    oa, ra, _, _ = run(2, 0, half)
+    ob, rb, _, _ = run(2, half, n)
+    assert torch.equal(torch.cat([oa, ob]), o2) and torch.equal(torch.cat([ra, rb]), r2)  # shards == whole

@@ -1,0 +1,154 @@
+"""CPU tests of the host side: packing, climate groups, sampling order, ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from weather2alert_b200 import schema, synthetic
+from weather2alert_b200.datautils import ClimateGroups, get_similar_counties
+from weather2alert_b200.sampling import EpisodeSampler
+from weather2alert_b200.store import (COEF_STRIDE, FeatureStore, RewardWeights, coef_pos_other,
+                                      coef_pos_table, xobs_pos)
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_schema_matches_reference_feature_names(golden):
+    names = golden.meta[0]["episodes"][0]["feature_names"]
+    assert list(schema.OBS_NAMES) == names
+    assert len(schema.TABLE_REWARD_SLOTS) == 24 and schema.OBS_DIM == 29
+
+
+def test_pack_layouts_round_trip(golden):
+    store, w = golden.store(), golden.weights("std")
+    S, Y, T = store.shape
+    xrew = store.pack_xrew().reshape(S, Y, T, 24)
+    for u, slot in enumerate(schema.TABLE_REWARD_SLOTS):
+        np.testing.assert_array_equal(xrew[..., u], store.feat[..., slot])
+    xobs = store.pack_xobs().reshape(S, Y, T, 32)
+    for slot in range(27):
+        np.testing.assert_array_equal(xobs[..., xobs_pos(slot)], store.feat[..., slot].astype(np.float32))
+    np.testing.assert_array_equal(xobs[..., xobs_pos(27)], store.sig_code)
+    used = {xobs_pos(s) for s in range(28)}
+    assert len(used) == 28 and all((xobs[..., p] == 0).all() for p in range(32) if p not in used)
+    packed = w.pack().reshape(len(w.fips_list), w.n_samples, COEF_STRIDE)
+    seen = set()
+    for h in (0, 1):
+        for u, slot in enumerate(schema.TABLE_REWARD_SLOTS):
+            np.testing.assert_array_equal(packed[:, :, coef_pos_table(u, h)], w.coef[:, :, h, slot].T)
+            seen.add(coef_pos_table(u, h))
+        for q, slot in enumerate((23, 24, 25, 27)):
+            np.testing.assert_array_equal(packed[:, :, coef_pos_other(q, h)], w.coef[:, :, h, slot].T)
+            seen.add(coef_pos_other(q, h))
+    assert len(seen) == 56 and all((packed[..., p] == 0).all() for p in range(64) if p not in seen)
+
+
+def test_store_frames_round_trip(tmp_path, golden):
+    store, w = golden.store(), golden.weights("std")
+    synthetic.write_reference_files(store, w, str(tmp_path))
+    again = FeatureStore.from_parquet_dir(str(tmp_path))
+    assert again.fips == store.fips and again.years == store.years and again.sig_labels == store.sig_labels
+    np.testing.assert_array_equal(again.n_days, store.n_days)
+    np.testing.assert_array_equal(again.feat, store.feat)
+    np.testing.assert_array_equal(again.sig_code, store.sig_code)
+    assert again.conf_fips == store.conf_fips and again.conf_zone == store.conf_zone
+    w2 = RewardWeights.from_dir(str(tmp_path))
+    assert w2.fips_list == w.fips_list
+    np.testing.assert_array_equal(w2.coef, w.coef)
+
+
+def test_weights_without_fips_list_raise_keyerror(tmp_path, golden):
+    import yaml
+
+    synthetic.write_reference_files(golden.store(), golden.weights("std"), str(tmp_path))
+    with open(tmp_path / "config.yaml", "w") as fh:
+        yaml.safe_dump({"name": "no_list"}, fh)
+    with pytest.raises(KeyError):  # env.py:75
+        RewardWeights.from_dir(str(tmp_path))
+
+
+def test_climate_groups_match_reference_helper(golden):
+    groups = ClimateGroups(golden.conf_fips, golden.conf_zone, golden.fips_list)
+    for f, want in golden.similar.items():
+        assert get_similar_counties(f, golden.conf_fips, golden.conf_zone) == want
+        assert groups.similar(f) == [x for x in want if x in golden.fips_list]  # env.py:116
+    with pytest.raises(KeyError):
+        groups.similar("99999")
+    # western states collapse to one group whatever their zone (datautils.py:113-120)
+    assert set(golden.similar["06037"]) >= {"04013", "06001", "06037", "06073", "53033", "20173", "08031"}
+
+
+def test_sampler_reproduces_reference_rng_draws(golden):
+    """Same numpy calls in the same order as env.py:143-160 -> same location/year/sample."""
+    store = golden.store()
+    checked = 0
+    for sc in golden.meta:
+        w = golden.weights(sc["weights"])
+        sampler = EpisodeSampler(store, w, sc["ctor"].get("years"))
+        assert [int(y) for y in sampler.valid_years] == sc["valid_years"]
+        for ep in sc["episodes"]:
+            kw = ep["reset"]
+            rng = np.random.default_rng(kw["seed"])
+            aug = kw.get("similar_climate_counties", sc["ctor"].get("similar_climate_counties", False))
+            d = sampler.draw_reference(rng, kw.get("location"), aug)
+            assert d["location"] + "_" + str(d["year"]) == ep["episode_index"]
+            assert d["info_location"] == ep["location"]
+            assert d["location_index"] == ep["location_index"]
+            assert d["coef_index"] == ep["coef_index"]
+            assert int(store.n_days[d["s"], d["y"]]) == ep["n_days"]
+            checked += 1
+    assert checked == 74
+
+
+def test_sampler_errors_follow_the_reference(golden):
+    sampler = EpisodeSampler(golden.store(), golden.weights("std"))
+    rng = np.random.default_rng(0)
+    with pytest.raises(ValueError):  # list.index, env.py:121
+        sampler.draw_reference(rng, "99999", False)
+    with pytest.raises(ValueError):  # in the data, not in the weights' county list
+        sampler.draw_reference(rng, "06001", False)
+    with pytest.raises(KeyError):  # (fips, year) not in the data, env.py:127
+        EpisodeSampler(golden.store(), golden.weights("std"), years=[1999]).draw_reference(rng, "06037", False)
+
+
+def test_bulk_sampler_ranges(golden):
+    sampler = EpisodeSampler(golden.store(), golden.weights("std"))
+    rng = np.random.default_rng(1)
+    s = sampler.draw_bulk(rng, 5000, None, augment=True)
+    assert s["loc"].dtype == np.int32 and len(s["loc"]) == 5000
+    assert (s["coef_col"] >= 0).all() and (s["coef_col"] < sampler.n_similar[s["list_idx"]]).all()
+    assert (s["coef_idx"] >= 0).all() and (s["coef_idx"] < 12).all()
+    assert set(np.unique(s["year"])) == {0, 1, 2}
+    np.testing.assert_array_equal(s["loc"], sampler.list_to_data[s["list_idx"]])
+    s = sampler.draw_bulk(rng, 10, "06037", augment=False)
+    assert (s["coef_col"] == golden.fips_list.index("06037")).all()
+    with pytest.raises(ValueError):
+        sampler.draw_bulk(rng, 10, "99999")
+
+
+def test_library_exports_every_declared_symbol():
+    from weather2alert_b200 import _lib
+
+    header = open(os.path.join(REPO, "include", "w2a.h")).read()
+    declared = set(re.findall(r"\b(w2a_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # ImportError if the extension was not built
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.w2a_version() == 100
+    assert lib.w2a_state_bytes(10) == 160
+    # error paths that need no GPU
+    assert lib.w2a_create(0, None) == -1
+    assert b"NULL" in lib.w2a_last_error(None)
+    assert lib.w2a_destroy(None) == 0
+
+
+def test_no_product_module_imports_the_oracle():
+    pkg = os.path.join(REPO, "weather2alert_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f

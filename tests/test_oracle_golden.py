@@ -71,3 +71,28 @@ def test_similar_counties_match_reference_helper(golden):
         assert orc.similar_counties(f, golden.conf_fips, golden.conf_zone) == want
     with pytest.raises(KeyError):
         orc.similar_counties("99999", golden.conf_fips, golden.conf_zone)
+
+
+def test_c_oracle_matches_reference(golden):
+    """oracle/c/heat_oracle.c (the cpu_baseline port) replays the same 74 reference episodes."""
+    from oracle import c_oracle
+
+    if not c_oracle.available():
+        pytest.skip("oracle/_build/libheat_oracle.so not built (run __graft_entry__.build())")
+    for wname in ("std", "large"):
+        eps = [ep for sc, ep in golden.all_episodes() if sc["weights"] == wname]
+        refs = [golden.episode(ep["key"]) for ep in eps]
+        co = c_oracle.COracle(golden.feat, golden.sig_code, golden.n_days, golden.coef[wname], len(eps))
+        obs = co.reset([golden.fips.index(ep["episode_index"].split("_")[0]) for ep in eps],
+                       [golden.years.index(int(ep["episode_index"].split("_")[1])) for ep in eps],
+                       [ep["location_index"] for ep in eps], [ep["coef_index"] for ep in eps],
+                       [ep["budget"] for ep in eps])
+        np.testing.assert_array_equal(obs, np.stack([r["obs0"] for r in refs]))
+        for i in range(max(len(r["actions"]) for r in refs)):
+            act = np.array([r["actions"][i] if i < len(r["actions"]) else 0 for r in refs])
+            obs, rew, done, rem, atb = co.step(act)
+            for j, r in enumerate(refs):
+                if i < len(r["actions"]):
+                    np.testing.assert_array_equal(obs[j], r["obs"][i])
+                    assert rew[j] == pytest.approx(r["reward"][i], rel=REWARD_RTOL, abs=1e-300)
+                    assert bool(done[j]) == bool(r["done"][i]) and rem[j] == r["rem"][i] and bool(atb[j]) == bool(r["atb"][i])

@@ -1,0 +1,153 @@
+"""Device-side core: HBM-resident tables + the reset/step launches, on torch tensors.
+
+PyTorch is plumbing here (device memory, the current stream); the work is done by the
+sm_100a kernels behind the C ABI.  Mirrors the data-holding half of
+`HeatAlertEnv.__init__` (`/root/reference/src/weather2alert/env.py:20-105`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .store import FeatureStore, RewardWeights
+
+_ACT_DTYPES = {torch.uint8: _lib.ACT_U8, torch.bool: _lib.ACT_U8, torch.int32: _lib.ACT_I32, torch.int64: _lib.ACT_I64}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class HeatAlertCore:
+    """One C context on one GPU with the feature store and coefficient tables installed."""
+
+    def __init__(self, store: FeatureStore, weights: RewardWeights, device="cuda:0"):
+        self._lib = _lib.lib()  # raises ImportError when the extension is not built
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("HeatAlertCore needs a CUDA device; there is no CPU path")
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA is not available; weather2alert_b200 has no CPU fallback")
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        self.store, self.weights = store, weights
+        S, Y, T = store.shape
+        self.S, self.Y, self.T = S, Y, T
+        self.P, self.Sw = weights.n_samples, len(weights.fips_list)
+        dev = self.device
+        self.xrew = torch.from_numpy(store.pack_xrew()).to(dev)
+        self.xobs = torch.from_numpy(store.pack_xobs()).to(dev)
+        self.n_days = torch.from_numpy(np.ascontiguousarray(store.n_days.reshape(-1))).to(dev)
+        self.budget0 = torch.from_numpy(np.ascontiguousarray(store.budget0.reshape(-1))).to(dev)
+        self.w = torch.from_numpy(weights.pack()).to(dev)
+        ctx = C.c_void_p()
+        _lib.check(self._lib.w2a_create(index, C.byref(ctx)))
+        self.ctx = ctx
+        _lib.check(self._lib.w2a_set_features(ctx, _ptr(self.xrew), _ptr(self.xobs), _ptr(self.n_days),
+                                              _ptr(self.budget0), S, Y, T), ctx)
+        _lib.check(self._lib.w2a_set_coefs(ctx, _ptr(self.w), self.P, self.Sw), ctx)
+
+    def __del__(self):
+        ctx = getattr(self, "ctx", None)
+        if ctx:
+            try:
+                self._lib.w2a_destroy(ctx)
+            except Exception:
+                pass
+            self.ctx = None
+
+    # ---- buffers ---------------------------------------------------------------------
+    def alloc_state(self, n: int) -> torch.Tensor:
+        return torch.zeros(int(self._lib.w2a_state_bytes(n)), dtype=torch.uint8, device=self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_dev(self, name, t, dtype=None, numel=None):
+        if t is None:
+            return
+        if not t.is_cuda or t.device != self.device or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous tensor on {self.device}")
+        if dtype is not None and t.dtype not in (dtype if isinstance(dtype, tuple) else (dtype,)):
+            raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+        if numel is not None and t.numel() != numel:
+            raise ValueError(f"{name} must have {numel} elements, got {t.numel()}")
+
+    # ---- launches --------------------------------------------------------------------
+    def reset(self, state, obs, loc, year, coef_col, coef_idx, budget=None, mask=None, remaining=None):
+        n = loc.numel()
+        for name, t in (("loc", loc), ("year", year), ("coef_col", coef_col), ("coef_idx", coef_idx),
+                        ("budget", budget), ("remaining", remaining)):
+            self._check_dev(name, t, torch.int32, n)
+        self._check_dev("mask", mask, (torch.uint8, torch.bool), n)
+        self._check_dev("obs", obs, torch.float32, n * _lib.OBS_DIM)
+        self._check_dev("state", state, torch.uint8, n * 16)
+        _lib.check(self._lib.w2a_reset(self.ctx, self._stream(), n, _ptr(loc), _ptr(year), _ptr(coef_col),
+                                       _ptr(coef_idx), _ptr(budget), _ptr(mask), _ptr(state), _ptr(obs),
+                                       _ptr(remaining)), self.ctx)
+
+    def step(self, state, action, obs, reward, terminated, remaining=None, at_budget=None,
+             variant=_lib.STEP_AUTO):
+        n = action.numel()
+        if action.dtype not in _ACT_DTYPES:
+            raise TypeError(f"action dtype {action.dtype} not supported (uint8/bool/int32/int64)")
+        self._check_dev("action", action, None, n)
+        self._check_dev("obs", obs, torch.float32, n * _lib.OBS_DIM)
+        self._check_dev("state", state, torch.uint8, n * 16)
+        self._check_dev("reward", reward, torch.float32, n)
+        self._check_dev("terminated", terminated, (torch.uint8, torch.bool), n)
+        self._check_dev("remaining", remaining, torch.int32, n)
+        self._check_dev("at_budget", at_budget, (torch.uint8, torch.bool), n)
+        _lib.check(self._lib.w2a_step(self.ctx, self._stream(), n, _ptr(action), _ACT_DTYPES[action.dtype],
+                                      _ptr(state), _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(remaining),
+                                      _ptr(at_budget), variant), self.ctx)
+
+    def bind_step(self, state, obs, reward, terminated, remaining=None, at_budget=None,
+                  variant=_lib.STEP_AUTO, action_dtype=torch.uint8):
+        """Validate the persistent buffers once and return `f(action_tensor)` that only
+        performs the C call (the per-step host cost of a rollout loop)."""
+        n = reward.numel()
+        self._check_dev("obs", obs, torch.float32, n * _lib.OBS_DIM)
+        self._check_dev("state", state, torch.uint8, n * 16)
+        self._check_dev("reward", reward, torch.float32, n)
+        self._check_dev("terminated", terminated, (torch.uint8, torch.bool), n)
+        self._check_dev("remaining", remaining, torch.int32, n)
+        self._check_dev("at_budget", at_budget, (torch.uint8, torch.bool), n)
+        fn, ctx, check = self._lib.w2a_step, self.ctx, _lib.check
+        adt = _ACT_DTYPES[action_dtype]
+        args = (_ptr(state), _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(remaining), _ptr(at_budget), variant)
+        stream = self._stream
+        device = self.device
+
+        def step(action):
+            if action.dtype != action_dtype or action.numel() != n or action.device != device:
+                raise ValueError(f"bound step expects {n} actions of dtype {action_dtype} on {device}")
+            rc = fn(ctx, stream(), n, C.c_void_p(action.data_ptr()), adt, *args)
+            if rc:
+                check(rc, ctx)
+
+        return step
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.w2a_launch_count(self.ctx))
+
+    # ---- host-buffer entry points (numpy in / numpy out) --------------------------------
+    def host_envs_create(self, n: int):
+        _lib.check(self._lib.w2a_host_envs_create(self.ctx, n), self.ctx)
+        self._host_n = n
+
+    def reset_host(self, loc, year, coef_col, coef_idx, obs, budget=None, mask=None, remaining=None):
+        def p(a):
+            return None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        _lib.check(self._lib.w2a_reset_host(self.ctx, p(loc), p(year), p(coef_col), p(coef_idx), p(budget),
+                                            p(mask), p(obs), p(remaining)), self.ctx)
+
+    def step_host(self, action, obs, reward, terminated, remaining=None, at_budget=None):
+        def p(a):
+            return None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        _lib.check(self._lib.w2a_step_host(self.ctx, p(action), p(obs), p(reward), p(terminated), p(remaining),
+                                           p(at_budget)), self.ctx)

@@ -35,6 +35,7 @@ struct HostEnvs {
 };
 
 char g_create_error[512] = "";
+constexpr int kMaxKernels = 16;
 
 }  // namespace
 
@@ -46,6 +47,9 @@ struct w2a_ctx {
   bool have_coefs = false;
   int64_t launches = 0;
   HostEnvs* host = nullptr;
+  const void* occ_key[kMaxKernels] = {};  // occupancy (CTAs per SM) of each kernel launched so far
+  int occ_val[kMaxKernels] = {};
+  int n_occ = 0;
   char err[512] = "";
 };
 
@@ -71,9 +75,18 @@ int fail(w2a_ctx* ctx, int code, const char* fmt, ...) {
 // more than the work needs; the kernels walk the envs with a grid-stride loop.
 template <typename K>
 int grid_for(w2a_ctx* ctx, K kernel, int block, int64_t work_items_per_block, int64_t n, int* grid) {
+  const void* key = reinterpret_cast<const void*>(kernel);
   int per_sm = 0;
-  W2A_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
-  if (per_sm < 1) per_sm = 1;
+  for (int i = 0; i < ctx->n_occ; ++i)
+    if (ctx->occ_key[i] == key) per_sm = ctx->occ_val[i];
+  if (per_sm == 0) {  // asked once per kernel and context
+    W2A_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (ctx->n_occ < kMaxKernels) {
+      ctx->occ_key[ctx->n_occ] = key;
+      ctx->occ_val[ctx->n_occ++] = per_sm;
+    }
+  }
   const int64_t need = (n + work_items_per_block - 1) / work_items_per_block;
   const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
   *grid = static_cast<int>(std::max<int64_t>(1, std::min(need, cap)));
@@ -363,6 +376,8 @@ int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward
   const int64_t n = h->n;
   uint2* sstat = plane_static(h->state);
   uint2* smut = plane_mut(h->state, n);
+  // one kernel variant for the whole batch, so that chunking never changes a result bit
+  const int variant = n < 32768 ? W2A_STEP_THREAD : W2A_STEP_COOP;
   int ci = 0;
   for (int64_t c0 = 0; c0 < n; c0 += kHostChunk, ++ci) {
     const int64_t m = std::min(kHostChunk, n - c0);
@@ -372,7 +387,7 @@ int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward
     int rc = step_planes(ctx, st, m, h->action + c0, W2A_ACT_U8, sstat + c0, smut + c0,
                          h->obs + c0 * W2A_OBS_DIM, h->reward + c0, h->terminated + c0,
                          remaining ? h->remaining + c0 : nullptr, at_budget ? h->at_budget + c0 : nullptr,
-                         W2A_STEP_AUTO);
+                         variant);
     if (rc) return rc;
     W2A_CUDA(ctx, cudaMemcpyAsync(obs + c0 * W2A_OBS_DIM, h->obs + c0 * W2A_OBS_DIM,
                                   um * W2A_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -60,8 +60,13 @@ class FeatureStore:
     sig_labels: list[str] = field(default_factory=list)
     conf_fips: list[str] = field(default_factory=list)  # confounders frame, row order
     conf_zone: list[str] = field(default_factory=list)
+    #: years in order of first appearance in the data = the reference's default
+    #: `valid_years` (env.py:104-105); None = ascending
+    year_order: list[int] | None = None
 
     def __post_init__(self):
+        if self.year_order is None:
+            self.year_order = [int(y) for y in self.years]
         self.fips_index = {f: i for i, f in enumerate(self.fips)}
         self.year_index = {int(y): i for i, y in enumerate(self.years)}
 
@@ -103,6 +108,7 @@ class FeatureStore:
             raise KeyError(f"feature store is missing columns {missing}")
         # `merged.loc[(fips, year)]` (env.py:127) yields the rows of a group in file order,
         # so group with a stable sort and keep the order inside each group untouched
+        year_order = [int(y) for y in merged.year.unique()]
         merged = merged.sort_values(["fips", "year"], kind="stable")
         fips = sorted(merged.fips.unique().tolist())
         years = sorted(int(y) for y in merged.year.unique())
@@ -135,6 +141,7 @@ class FeatureStore:
             sig_labels=labels,
             conf_fips=[str(f) for f in confounders.fips.tolist()],
             conf_zone=[str(z) for z in confounders.ba_zone.tolist()],
+            year_order=year_order,
         )
 
     @classmethod

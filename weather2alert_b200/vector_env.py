@@ -1,0 +1,257 @@
+"""`HeatAlertVectorEnv` -- N independent HeatAlertEnv episodes stepped by one kernel launch.
+
+Follows the `gymnasium.vector.VectorEnv` surface (`num_envs`, `single_observation_space`,
+`single_action_space`, `reset(seed=, options=)`, `step(actions)`), but every array it
+returns is a torch CUDA tensor: observations ``float32[N,29]``, rewards ``float32[N]``,
+terminations / truncations ``bool[N]``, and an `infos` dict of tensors.  The reference
+has no vector wrapper (users wrap `HeatAlertEnv` with Gymnasium/SB3);
+per-env semantics are exactly those of `/root/reference/src/weather2alert/env.py:133-262`.
+
+Episode sampling (`env.py:143-177`: county, similar-county index, year, posterior sample,
+budget) is drawn on the device from one seeded torch Generator, so a reset costs a few
+tiny launches and never stalls the stream; pass ``options={"index_streams": ...}`` to
+supply host-sampled streams instead (that is how trajectories are reproduced against the
+reference, whose own resets seed one PCG64 per env).
+
+Autoreset is SAME_STEP: an env that terminates is reset inside the same `step` call (the
+returned observation is the first one of its next episode; the reference's terminal
+observation is just the previous one, quirk Q2).  Termination is ``t >= n_days - 1``,
+a function of the sampled episode only, so when all summers have the same length the
+host knows the schedule and autoreset needs no device->host synchronisation.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, schema
+from ._gym import spaces
+from .core import HeatAlertCore
+from .sampling import EpisodeSampler
+from .store import FeatureStore, RewardWeights
+
+
+class HeatAlertVectorEnv:
+    metadata = {"autoreset_mode": "same_step"}
+
+    def __init__(
+        self,
+        num_envs: int,
+        weights: RewardWeights | str = "nn_full_medicare_all",
+        store: FeatureStore | None = None,
+        years: list | None = None,
+        similar_climate_counties: bool = False,
+        budget: int | None = None,
+        data_dir: str | None = None,
+        split: str = "65k",
+        device: str = "cuda:0",
+        seed: int | None = None,
+        autoreset: bool = True,
+        core: HeatAlertCore | None = None,
+        step_variant: int = _lib.STEP_AUTO,
+    ):
+        if core is None:
+            if store is None or not isinstance(weights, RewardWeights):
+                from .loading import load_store, load_weights
+
+                store = store if store is not None else load_store(data_dir, split)
+                weights = weights if isinstance(weights, RewardWeights) else load_weights(weights, data_dir)
+            core = HeatAlertCore(store, weights, device)
+        self.core = core
+        self.store, self.weights = core.store, core.weights
+        self.device = core.device
+        self.num_envs = int(num_envs)
+        self.similar_climate_counties = similar_climate_counties
+        self.budget = budget
+        self.autoreset = autoreset
+        self.step_variant = step_variant
+        self.sampler = EpisodeSampler(self.store, self.weights, years)
+        self.fips_list = self.sampler.fips_list
+        self.single_observation_space = spaces.Box(-np.inf, np.inf, (schema.OBS_DIM,), np.float32)
+        self.single_action_space = spaces.Discrete(2)
+        self.observation_space = spaces.Box(-np.inf, np.inf, (self.num_envs, schema.OBS_DIM), np.float32)
+        self.action_space = self.single_action_space
+        self.feature_names = list(schema.OBS_NAMES)
+
+        n, dev = self.num_envs, self.device
+        self._gen = torch.Generator(device=dev)
+        self._gen.manual_seed(int(seed) if seed is not None else int(np.random.randint(0, 2**31 - 1)))
+        self._host_rng = np.random.default_rng(seed)
+        # device copies of the sampler's integer tables
+        sp = self.sampler
+        self._list_to_data = torch.from_numpy(sp.list_to_data).to(dev)
+        self._n_similar = torch.from_numpy(sp.n_similar.astype(np.int64)).to(dev)
+        self._valid_year_idx = torch.from_numpy(sp._valid_year_idx).to(dev)
+        nd = self.store.n_days
+        ok_c = sp.list_to_data >= 0
+        ok_y = sp._valid_year_idx >= 0
+        sub = nd[np.ix_(sp.list_to_data[ok_c], sp._valid_year_idx[ok_y])]
+        # every (county of the weights, valid year) exists -> device draws cannot hit a missing episode
+        self._all_episodes_exist = bool(ok_c.all() and ok_y.all() and (sub > 0).all())
+        self._uniform_days = int(sub.flat[0]) if sub.size and (sub == sub.flat[0]).all() else None
+        self._n_days_dev = core.n_days  # uint8 [S*Y]
+
+        self._state = core.alloc_state(n)
+        self._obs = torch.zeros((n, schema.OBS_DIM), dtype=torch.float32, device=dev)
+        self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._term = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._trunc = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._rem = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._atb = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._bound = {}
+        self._idx = {}        # index streams of the most recent draw (device int32)
+        self._list_idx = torch.zeros(n, dtype=torch.int32, device=dev)  # county (fips_list index) per env
+        self._term_at = None  # device int64[n]: step number at which each env terminates
+        self._step_no = 0
+        self._next_term = None
+        self._reset_opts = {}
+
+    # ---- sampling -------------------------------------------------------------------------------
+    def _randint(self, high, n):
+        return torch.randint(0, int(high), (n,), generator=self._gen, device=self.device)
+
+    def _draw(self):
+        """Index streams for all N envs as device int32 tensors."""
+        n, dev, o = self.num_envs, self.device, self._reset_opts
+        sp = self.sampler
+        if "index_streams" in o:
+            src = o["index_streams"]
+            s = {k: torch.as_tensor(np.ascontiguousarray(src[k], dtype=np.int32)).to(dev)
+                 for k in ("loc", "year", "coef_col", "coef_idx")}
+            if "budget" in src:
+                s["budget"] = torch.as_tensor(np.ascontiguousarray(src["budget"], dtype=np.int32)).to(dev)
+            s["list_idx"] = (torch.as_tensor(np.ascontiguousarray(src["list_idx"], dtype=np.int32)).to(dev)
+                             if "list_idx" in src else s["coef_col"])
+            nd = self.store.n_days[np.asarray(src["loc"]), np.asarray(src["year"])]
+            if (nd == 0).any():
+                bad = int(np.argmax(nd == 0))
+                raise KeyError((self.store.fips[int(src["loc"][bad])], self.store.years[int(src["year"][bad])]))
+            return s
+        augment = o.get("similar_climate_counties", self.similar_climate_counties)
+        location = o.get("location")
+        if location is None:
+            list_idx = self._randint(len(sp.fips_list), n)  # env.py:151-152
+        elif isinstance(location, str):
+            list_idx = torch.full((n,), sp.fips_list.index(location), dtype=torch.int64, device=dev)  # ValueError
+        else:
+            h = sp.draw_bulk(self._host_rng, n, location, False)["list_idx"]
+            list_idx = torch.from_numpy(h.astype(np.int64)).to(dev)
+        loc = self._list_to_data[list_idx]
+        if augment:  # index inside the similar-county list (env.py:117; Q6)
+            n_c = self._n_similar[list_idx]
+            u = torch.rand(n, generator=self._gen, device=dev, dtype=torch.float64)
+            coef_col = torch.minimum((u * n_c).long(), n_c - 1)
+        else:
+            coef_col = list_idx  # env.py:121
+        year = self._valid_year_idx[self._randint(len(sp.valid_years), n)]  # env.py:125
+        coef_idx = self._randint(sp.n_samples, n)  # env.py:160
+        if not self._all_episodes_exist or augment:
+            bad = (loc < 0) | (year < 0)
+            if augment:
+                bad |= self._n_similar[list_idx] <= 0
+            bad |= self._n_days_dev[(loc.clamp(min=0) * self.core.Y + year.clamp(min=0))] == 0
+            if bool(bad.any()):  # the reference raises KeyError at env.py:127 / datautils.py:123
+                b = int(torch.nonzero(bad)[0])
+                raise KeyError((sp.fips_list[int(list_idx[b])], int(year[b])))
+        s = dict(loc=loc.int(), year=year.int(), coef_col=coef_col.int(), coef_idx=coef_idx.int(),
+                 list_idx=list_idx.int())
+        budget = o.get("budget", self.budget)
+        if budget is not None or o.get("sample_budget", False):
+            if budget is None:
+                b = self.core.budget0[(loc * self.core.Y + year)].long()
+            else:
+                b = torch.as_tensor(np.broadcast_to(np.asarray(budget, dtype=np.int64), (n,)).copy()).to(dev)
+            if o.get("sample_budget", False):  # env.py:172-177, per env, without the sticky compounding (Q8)
+                u = torch.rand(n, generator=self._gen, device=dev, dtype=torch.float64)
+                if o.get("sample_budget_type", "less_than") == "less_than":
+                    lo, hi = torch.zeros_like(b), b + 1
+                else:
+                    lo, hi = (0.5 * b.double()).long(), (1.5 * b.double() + 1).long()
+                b = lo + torch.minimum((u * (hi - lo)).long(), hi - lo - 1)
+            s["budget"] = b.int()
+        return s
+
+    # ---- reset --------------------------------------------------------------------------------
+    def reset(self, *, seed: int | None = None, options: dict | None = None):
+        """`options` keys: `location` (FIPS, or a sequence of N), `similar_climate_counties`,
+        `budget` (int or sequence), `sample_budget`, `sample_budget_type`, or `index_streams`
+        (dict of int arrays `loc`, `year`, `coef_col`, `coef_idx`[, `budget`, `list_idx`])."""
+        if seed is not None:
+            self._gen.manual_seed(int(seed))
+            self._host_rng = np.random.default_rng(seed)
+        self._reset_opts = dict(options or {})
+        self._step_no = 0
+        self._reset_subset(None)
+        return self._obs, self._infos()
+
+    def _reset_subset(self, mask):
+        s = self._draw()
+        self._idx = s
+        self.core.reset(self._state, self._obs, s["loc"], s["year"], s["coef_col"], s["coef_idx"],
+                        budget=s.get("budget"), mask=mask, remaining=self._rem)
+        if mask is None:
+            self._list_idx = s["list_idx"]
+            self._atb.zero_()
+        else:
+            self._list_idx = torch.where(mask.bool(), s["list_idx"], self._list_idx)
+        if self._uniform_days is not None:
+            if mask is None:  # lockstep: the host knows the whole schedule
+                self._term_at = None
+                self._next_term = self._step_no + self._uniform_days
+                return
+        ends = self._step_no + self._n_days_dev[(s["loc"].long() * self.core.Y + s["year"].long())].long()
+        if mask is None or self._term_at is None:
+            self._term_at = ends if mask is None else torch.where(
+                mask.bool(), ends, torch.full_like(ends, self._next_term))
+        else:
+            self._term_at = torch.where(mask.bool(), ends, self._term_at)
+        self._next_term = int(self._term_at.min())  # one small sync per reset, only for ragged summers
+
+    # ---- step -----------------------------------------------------------------------------------
+    def step(self, actions: torch.Tensor):
+        if self._next_term is None:
+            raise RuntimeError("call reset() before step()")
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions), device=self.device)
+        if actions.device != self.device:
+            actions = actions.to(self.device)
+        if actions.dtype == torch.bool:
+            actions = actions.view(torch.uint8)
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        fn = self._bound.get(actions.dtype)
+        if fn is None:
+            fn = self._bound[actions.dtype] = self.core.bind_step(
+                self._state, self._obs, self._reward, self._term.view(torch.uint8), self._rem,
+                self._atb.view(torch.uint8), variant=self.step_variant, action_dtype=actions.dtype)
+        fn(actions)
+        self._step_no += 1
+        if self.autoreset and self._step_no >= self._next_term:
+            if self._term_at is None:
+                self._reset_subset(None)
+            else:
+                self._reset_subset((self._term_at <= self._step_no).to(torch.uint8))
+        return self._obs, self._reward, self._term, self._trunc, self._infos()
+
+    def _infos(self):
+        return {"remaining_budget": self._rem, "at_budget": self._atb, "location_index": self._list_idx}
+
+    # ---- checkpoint / resume ----------------------------------------------------------------------
+    def state_dict(self):
+        return {"state": self._state.clone(), "obs": self._obs.clone(), "step_no": self._step_no,
+                "term_at": None if self._term_at is None else self._term_at.clone(),
+                "next_term": self._next_term, "list_idx": self._list_idx.clone(),
+                "gen": self._gen.get_state(), "host_rng": self._host_rng.bit_generator.state}
+
+    def load_state_dict(self, sd):
+        self._state.copy_(sd["state"])
+        self._obs.copy_(sd["obs"])
+        self._step_no = int(sd["step_no"])
+        self._term_at = None if sd["term_at"] is None else sd["term_at"].clone()
+        self._next_term = sd["next_term"]
+        self._list_idx = sd["list_idx"].clone()
+        self._gen.set_state(sd["gen"])
+        self._host_rng.bit_generator.state = sd["host_rng"]
+
+    def close(self):
+        self.core = None
