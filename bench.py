@@ -185,7 +185,7 @@ def run_ours(args):
         core.reset(state, obs, idx["loc"], idx["year"], idx["coef_col"], idx["coef_idx"], remaining=rem)
 
     log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s: {n} envs, tables "
-        f"{(core.xrew.numel() * 8 + core.xobs.numel() * 4 + core.w.numel() * 4) / 1e6:.0f} MB")
+        f"{(core.x.numel() * 8 + core.w.numel() * 4) / 1e6:.0f} MB")
 
     # ---- device-resident throughput: `value` ---------------------------------------------------
     def run_steps(k, t):

@@ -39,10 +39,10 @@ extern "C" {
 /* Observation layout: 29 float32 slots per env, row-major [n, 29]; slot order is
  * `info["feature_names"]` of the reference (src/weather2alert/env.py:182-183). */
 #define W2A_OBS_DIM 29
-/* Device table row strides (see DESIGN.md "Data layout in HBM"). */
-#define W2A_XREW_STRIDE 24 /* float64 per day-row: reward features read from the table */
-#define W2A_XOBS_STRIDE 32 /* float32 per day-row: observation slots, lane-permuted */
-#define W2A_COEF_STRIDE 64 /* float32 per (county, posterior sample): 2 heads x 28, lane-permuted */
+/* Device table records (see DESIGN.md "Data layout in HBM"): both are 256 bytes, and the
+ * tables must be 128-byte aligned so that a record is exactly two cache lines. */
+#define W2A_X_STRIDE 32 /* float64 per day-row: 0..23 table reward features, 24 significance code, 25..31 zero */
+#define W2A_W_STRIDE 64 /* float32 per (county, posterior sample): (baseline, effectiveness) pairs */
 
 /* action_dtype */
 #define W2A_ACT_U8 0
@@ -71,18 +71,23 @@ int w2a_create(int device, w2a_ctx** out);
 int w2a_destroy(w2a_ctx* ctx);
 
 /* Install the HBM-resident feature store (replaces `self.merged`, env.py:49-56).
- *   xrew    dev float64 [S*Y*T, 24]  table-sourced reward features, slots 0..22 and 26
- *   xobs    dev float32 [S*Y*T, 32]  observation slots, float at 4*q+i holds slot 8*i+q
+ *   x       dev float64 [S*Y*T, 32]  one record per (county, year, day): positions 0..23 are
+ *                                    the reward features read from the table (observation slots
+ *                                    0..22 and 26, float64 as in the parquet files), position 24
+ *                                    the significance code (0.0 = none, shown as NaN; k = label
+ *                                    k), positions 25..31 must be 0.0
  *   n_days  dev uint8   [S*Y]        days in episode (county, year); 0 = no such episode
  *   budget0 dev int32   [S*Y]        historical `remaining_budget` of day 0 (env.py:169)
  * The tables are referenced, not copied, and must outlive their use.  S*Y*T < 2^24. */
-int w2a_set_features(w2a_ctx* ctx, const double* xrew, const float* xobs,
-                     const uint8_t* n_days, const int32_t* budget0, int S, int Y, int T);
+int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const int32_t* budget0,
+                     int S, int Y, int T);
 
 /* Install the posterior coefficient draws (replaces `self.baseline_coefs` /
  * `self.effectiveness_coefs`, env.py:77-82).
- *   w  dev float32 [S_w*P, 64]; vector (col*P + p) holds the 2x28 coefficients of county
- *      column `col`, posterior sample `p`, in the lane-permuted order of DESIGN.md. */
+ *   w  dev float32 [S_w*P, 64]; record (col*P + p) holds the coefficients of county column
+ *      `col`, posterior sample `p` as (baseline, effectiveness) pairs: floats 0..47 the 24
+ *      table features in record order, 48..55 must be 0, 56..63 alert_lag1, alert_streak,
+ *      remaining_budget, bias. */
 int w2a_set_coefs(w2a_ctx* ctx, const float* w, int P, int S_w);
 
 /* Bytes of the opaque per-env state for `n` envs (16 bytes per env, two SoA planes). */

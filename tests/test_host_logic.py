@@ -9,8 +9,8 @@ import pytest
 from weather2alert_b200 import schema, synthetic
 from weather2alert_b200.datautils import ClimateGroups, get_similar_counties
 from weather2alert_b200.sampling import EpisodeSampler
-from weather2alert_b200.store import (COEF_STRIDE, FeatureStore, RewardWeights, coef_pos_other,
-                                      coef_pos_table, xobs_pos)
+from weather2alert_b200.store import (W_STRIDE, X_SIG, X_STRIDE, FeatureStore, RewardWeights, coef_pos_other,
+                                      coef_pos_table)
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -24,25 +24,23 @@ def test_schema_matches_reference_feature_names(golden):
 def test_pack_layouts_round_trip(golden):
     store, w = golden.store(), golden.weights("std")
     S, Y, T = store.shape
-    xrew = store.pack_xrew().reshape(S, Y, T, 24)
+    x = store.pack_x().reshape(S, Y, T, X_STRIDE)
     for u, slot in enumerate(schema.TABLE_REWARD_SLOTS):
-        np.testing.assert_array_equal(xrew[..., u], store.feat[..., slot])
-    xobs = store.pack_xobs().reshape(S, Y, T, 32)
-    for slot in range(27):
-        np.testing.assert_array_equal(xobs[..., xobs_pos(slot)], store.feat[..., slot].astype(np.float32))
-    np.testing.assert_array_equal(xobs[..., xobs_pos(27)], store.sig_code)
-    used = {xobs_pos(s) for s in range(28)}
-    assert len(used) == 28 and all((xobs[..., p] == 0).all() for p in range(32) if p not in used)
-    packed = w.pack().reshape(len(w.fips_list), w.n_samples, COEF_STRIDE)
+        np.testing.assert_array_equal(x[..., u], store.feat[..., slot])
+    sig = x[..., X_SIG]
+    np.testing.assert_array_equal(np.where(sig == 0, np.nan, sig).astype(np.float32), store.sig_code)
+    assert (x[..., 25:] == 0).all() and np.isfinite(x).all()
+    packed = w.pack().reshape(len(w.fips_list), w.n_samples, W_STRIDE)
     seen = set()
     for h in (0, 1):
         for u, slot in enumerate(schema.TABLE_REWARD_SLOTS):
             np.testing.assert_array_equal(packed[:, :, coef_pos_table(u, h)], w.coef[:, :, h, slot].T)
             seen.add(coef_pos_table(u, h))
-        for q, slot in enumerate((23, 24, 25, 27)):
-            np.testing.assert_array_equal(packed[:, :, coef_pos_other(q, h)], w.coef[:, :, h, slot].T)
-            seen.add(coef_pos_other(q, h))
-    assert len(seen) == 56 and all((packed[..., p] == 0).all() for p in range(64) if p not in seen)
+        for k, slot in enumerate((23, 24, 25, 27)):
+            np.testing.assert_array_equal(packed[:, :, coef_pos_other(k, h)], w.coef[:, :, h, slot].T)
+            seen.add(coef_pos_other(k, h))
+    assert len(seen) == 56 and all((packed[..., p] == 0).all() for p in range(W_STRIDE) if p not in seen)
+    assert seen == set(range(48)) | set(range(56, 64))
 
 
 def test_store_frames_round_trip(tmp_path, golden):

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libw2a.so")
+# W2A_LIB_PATH selects another build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("W2A_LIB_PATH") or os.path.join(_HERE, "libw2a.so")
 
 W2A_OK = 0
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
@@ -24,7 +25,7 @@ SIGNATURES = {
     "w2a_last_error": (C.c_char_p, [_P]),
     "w2a_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "w2a_destroy": (C.c_int, [_P]),
-    "w2a_set_features": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
+    "w2a_set_features": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "w2a_set_coefs": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "w2a_state_bytes": (C.c_size_t, [C.c_int64]),
     "w2a_reset": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -38,16 +38,15 @@ class HeatAlertCore:
         self.S, self.Y, self.T = S, Y, T
         self.P, self.Sw = weights.n_samples, len(weights.fips_list)
         dev = self.device
-        self.xrew = torch.from_numpy(store.pack_xrew()).to(dev)
-        self.xobs = torch.from_numpy(store.pack_xobs()).to(dev)
+        self.x = torch.from_numpy(store.pack_x()).to(dev)
         self.n_days = torch.from_numpy(np.ascontiguousarray(store.n_days.reshape(-1))).to(dev)
         self.budget0 = torch.from_numpy(np.ascontiguousarray(store.budget0.reshape(-1))).to(dev)
         self.w = torch.from_numpy(weights.pack()).to(dev)
         ctx = C.c_void_p()
         _lib.check(self._lib.w2a_create(index, C.byref(ctx)))
         self.ctx = ctx
-        _lib.check(self._lib.w2a_set_features(ctx, _ptr(self.xrew), _ptr(self.xobs), _ptr(self.n_days),
-                                              _ptr(self.budget0), S, Y, T), ctx)
+        _lib.check(self._lib.w2a_set_features(ctx, _ptr(self.x), _ptr(self.n_days), _ptr(self.budget0),
+                                              S, Y, T), ctx)
         _lib.check(self._lib.w2a_set_coefs(ctx, _ptr(self.w), self.P, self.Sw), ctx)
 
     def __del__(self):

@@ -74,14 +74,16 @@ int fail(w2a_ctx* ctx, int code, const char* fmt, ...) {
 // Persistent-style grid: enough CTAs to fill every SM at the kernel's occupancy, never
 // more than the work needs; the kernels walk the envs with a grid-stride loop.
 template <typename K>
-int grid_for(w2a_ctx* ctx, K kernel, int block, int64_t work_items_per_block, int64_t n, int* grid) {
+int grid_for(w2a_ctx* ctx, K kernel, int block, size_t smem, int64_t work_items_per_block, int64_t n, int* grid) {
   const void* key = reinterpret_cast<const void*>(kernel);
   int per_sm = 0;
   for (int i = 0; i < ctx->n_occ; ++i)
     if (ctx->occ_key[i] == key) per_sm = ctx->occ_val[i];
   if (per_sm == 0) {  // asked once per kernel and context
-    W2A_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
-    if (per_sm < 1) per_sm = 1;
+    if (smem > 48 * 1024)
+      W2A_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    W2A_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+    if (per_sm < 1) return fail(ctx, W2A_E_CUDA, "kernel does not fit on an SM (block %d, %zu B shared)", block, smem);
     if (ctx->n_occ < kMaxKernels) {
       ctx->occ_key[ctx->n_occ] = key;
       ctx->occ_val[ctx->n_occ++] = per_sm;
@@ -97,13 +99,14 @@ template <int ADT>
 int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int variant) {
   int grid = 0;
   if (variant == W2A_STEP_THREAD) {
-    int rc = grid_for(ctx, w2a::step_thread_kernel<ADT>, 128, 128, a.n, &grid);
+    int rc = grid_for(ctx, w2a::step_thread_kernel<ADT>, 128, 0, 128, a.n, &grid);
     if (rc) return rc;
     w2a::step_thread_kernel<ADT><<<grid, 128, 0, st>>>(a);
   } else {
-    int rc = grid_for(ctx, w2a::step_coop_kernel<ADT>, 256, 256, a.n, &grid);
+    constexpr int kBlock = 32 * w2a::kCoopWarps;
+    int rc = grid_for(ctx, w2a::step_coop_kernel<ADT>, kBlock, w2a::kCoopSmemBytes, kBlock, a.n, &grid);
     if (rc) return rc;
-    w2a::step_coop_kernel<ADT><<<grid, 256, 0, st>>>(a);
+    w2a::step_coop_kernel<ADT><<<grid, kBlock, w2a::kCoopSmemBytes, st>>>(a);
   }
   ctx->launches++;
   W2A_CUDA(ctx, cudaGetLastError());
@@ -153,7 +156,7 @@ int reset_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const int32_t* loc, c
   a.remaining = remaining;
   a.n = static_cast<int>(n);
   int grid = 0;
-  int rc = grid_for(ctx, w2a::reset_kernel, 256, 256, n, &grid);
+  int rc = grid_for(ctx, w2a::reset_kernel, 256, 0, 256, n, &grid);
   if (rc) return rc;
   w2a::reset_kernel<<<grid, 256, 0, st>>>(a);
   ctx->launches++;
@@ -213,20 +216,18 @@ int w2a_destroy(w2a_ctx* ctx) {
   return W2A_OK;
 }
 
-int w2a_set_features(w2a_ctx* ctx, const double* xrew, const float* xobs, const uint8_t* n_days,
-                     const int32_t* budget0, int S, int Y, int T) {
+int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const int32_t* budget0, int S, int Y,
+                     int T) {
   if (!ctx) return W2A_E_INVALID;
-  if (!xrew || !xobs || !n_days || !budget0)
-    return fail(ctx, W2A_E_INVALID, "w2a_set_features: NULL table");
+  if (!x || !n_days || !budget0) return fail(ctx, W2A_E_INVALID, "w2a_set_features: NULL table");
   if (S <= 0 || Y <= 0 || T <= 0 || T > 255)
     return fail(ctx, W2A_E_INVALID, "w2a_set_features: bad shape S=%d Y=%d T=%d (T<=255)", S, Y, T);
   if (static_cast<int64_t>(S) * Y * T >= (int64_t{1} << 24))
     return fail(ctx, W2A_E_INVALID, "w2a_set_features: S*Y*T=%lld rows exceed the 24-bit row index",
                 static_cast<long long>(static_cast<int64_t>(S) * Y * T));
-  if ((reinterpret_cast<uintptr_t>(xrew) & 15) || (reinterpret_cast<uintptr_t>(xobs) & 15))
-    return fail(ctx, W2A_E_INVALID, "w2a_set_features: tables must be 16-byte aligned");
-  ctx->tb.xrew = xrew;
-  ctx->tb.xobs = xobs;
+  if (reinterpret_cast<uintptr_t>(x) & 127)
+    return fail(ctx, W2A_E_INVALID, "w2a_set_features: the table must be 128-byte aligned");
+  ctx->tb.x = x;
   ctx->tb.n_days = n_days;
   ctx->tb.budget0 = budget0;
   ctx->tb.S = S;
@@ -239,8 +240,10 @@ int w2a_set_features(w2a_ctx* ctx, const double* xrew, const float* xobs, const 
 int w2a_set_coefs(w2a_ctx* ctx, const float* w, int P, int S_w) {
   if (!ctx) return W2A_E_INVALID;
   if (!w || P <= 0 || S_w <= 0) return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: bad argument");
-  if (reinterpret_cast<uintptr_t>(w) & 15)
-    return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: table must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(w) & 127)
+    return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: the table must be 128-byte aligned");
+  if (static_cast<int64_t>(P) * S_w >= (int64_t{1} << 31))
+    return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: P*S_w too large");
   ctx->tb.w = w;
   ctx->tb.P = P;
   ctx->tb.Sw = S_w;

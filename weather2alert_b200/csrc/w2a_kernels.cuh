@@ -7,40 +7,47 @@
 //   * per-env state is two SoA planes of 8 bytes (static: episode row + coefficient
 //     vector; mutable: remaining budget + packed day/streak/14-day window), so a warp
 //     reads and writes it with fully coalesced 8-byte accesses;
-//   * the step kernel gives every env 8 lanes: the env's three table rows (float64
-//     reward features, float32 observation slots, float32 coefficient vector) are each
-//     one contiguous 128-256 B run read with 128-bit loads by those 8 lanes, the two
-//     28-term dot products are accumulated in float64 and folded with warp shuffles,
-//     and the 29-slot observation goes out as four contiguous 32-byte pieces;
-//   * tables are read through the read-only path and stay L2/L1 resident; the per-env
+//   * both tables are arrays of 256-byte, line-aligned records (one day-row of float64
+//     features; one float32 coefficient vector), so the gather of one env is exactly
+//     four 128-byte lines, each fetched by 8 lanes with one 128-bit load apiece;
+//   * the step kernel gives every env 8 lanes for that gather, accumulates the two
+//     28-term dot products in float64, folds the 8 partials through shared memory, and
+//     stages the 29-slot observations of a warp's 32 envs in shared memory so that they
+//     leave as one contiguous 3712-byte run of 128-bit streaming stores;
+//   * tables are read through the read-only path and stay L2 resident; the per-env
 //     streams (state, action, obs, reward, flags) use streaming (.cs) accesses so they
 //     do not evict the tables.
 #pragma once
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 namespace w2a {
 
 constexpr int kObsDim = 29;
-constexpr int kXrewStride = 24;
-constexpr int kXobsStride = 32;
-constexpr int kCoefStride = 64;
+constexpr int kXStride = 32;   // float64 per day-row record
+constexpr int kWStride = 64;   // float32 per coefficient record
+constexpr int kXSig = 24;      // record position of the significance code (0 = none)
+constexpr int kWOther = 56;    // first float of the non-table coefficients
 constexpr unsigned kFull = 0xffffffffu;
 // env.py:221 -- the reference divides by 152, not 153
 constexpr double kRewardScale = -1000.0 / 152.0;
 
 struct Tables {
-  const double* xrew;      // [R, 24] float64
-  const float* xobs;       // [R, 32] float32, float 4*q+i = slot 8*i+q
+  // [R, 32] float64: 0..23 = reward features read from the table (obs slots 0..22 and 26),
+  // 24 = significance code (0.0 = none, k = label k), 25..31 = 0.0
+  const double* x;
   const uint8_t* n_days;   // [S*Y]
   const int32_t* budget0;  // [S*Y]
-  const float* w;          // [Sw*P, 64] float32, lane-permuted
+  // [Sw*P, 64] float32: (baseline, effectiveness) pairs; 0..47 = the 24 table features,
+  // 48..55 = 0, 56..63 = alert_lag1, alert_streak, remaining_budget, bias
+  const float* w;
   int S, Y, T, P, Sw;
 };
 
 struct StepArgs {
   Tables tb;
-  const uint2* st_static;  // x: row0 (24 bit) | n_days << 24 ; y: coefficient vector index
+  const uint2* st_static;  // x: row0 (24 bit) | n_days << 24 ; y: coefficient record index
   uint2* st_mut;           // x: remaining budget (int32)      ; y: t | streak<<8 | win14<<16 | done<<30
   const void* action;
   float* obs;
@@ -66,7 +73,7 @@ struct ResetArgs {
   int n;
 };
 
-// ---- memory-access helpers ------------------------------------------------------------
+// ---- helpers --------------------------------------------------------------------------
 __device__ __forceinline__ uint2 ld_stream(const uint2* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(uint2* p, uint2 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
@@ -81,14 +88,11 @@ __device__ __forceinline__ int load_action(const void* a, int e) {
 // scipy.special.expit in float64, as used at env.py:211,218
 __device__ __forceinline__ double expit(double z) { return 1.0 / (1.0 + exp(-z)); }
 
-// position of a coefficient inside the 64-float lane-permuted vector
-//   table feature u (0..23: slots 0..22 and 26), head h: u < 16 -> 2u+h ; else 32+4(u-16)+h
-//   lane-q "other" term (q=0 lag1, 1 streak, 2 remaining budget, 3 bias), head h: 32+4q+2+h
-__host__ __device__ __forceinline__ int coef_pos_table(int u, int h) {
-  return u < 16 ? 2 * u + h : 32 + 4 * (u - 16) + h;
-}
-__host__ __device__ __forceinline__ int coef_pos_other(int q, int h) { return 32 + 4 * q + 2 + h; }
-__host__ __device__ __forceinline__ int xobs_pos(int slot) { return 4 * (slot & 7) + (slot >> 3); }
+// observation slot of table feature u (u = 0..23): slots 0..22, then 26 (issued_in_advance)
+__host__ __device__ __forceinline__ int slot_of_feature(int u) { return u < 23 ? u : 26; }
+// significance: record value 0.0 means "no alert" and is shown as NaN (the reference's
+// obs carries NaN there)
+__device__ __forceinline__ float sig_to_obs(float code) { return code == 0.f ? CUDART_NAN_F : code; }
 
 // ---- the integer alert-history transition (env.py:238-250, 256-260) ---------------------
 struct Transition {
@@ -130,13 +134,6 @@ __device__ __forceinline__ Transition advance(uint2 sv, uint2& mv, int a) {
   return o;
 }
 
-// reward = -1000/152 * sigmoid(z_b) * (1 - sigmoid(z_e) * [heat_qi > 0.5] * action)   (env.py:211-221)
-__device__ __forceinline__ float reward_from_logits(double zb, double ze, int gate, int act) {
-  const double baseline = expit(zb);
-  const double eff = (gate && act) ? expit(ze) : 0.0;
-  return static_cast<float>(kRewardScale * baseline * (1.0 - eff));
-}
-
 // =========================================================================================
 // step, variant THREAD: one thread per env.  The straightforward kernel: used for small
 // batches (launch-latency bound anyway) and as the in-tree cross-check of the COOP kernel.
@@ -151,60 +148,129 @@ __global__ void __launch_bounds__(128) step_thread_kernel(const StepArgs p) {
     const Transition tr = advance(sv, mv, a);
     st_stream(p.st_mut + e, mv);
 
-    const double* __restrict__ xr = p.tb.xrew + static_cast<size_t>(tr.row) * kXrewStride;
-    const float* __restrict__ wv = p.tb.w + static_cast<size_t>(sv.y) * kCoefStride;
-    double zb = 0.0, ze = 0.0;
+    const double* __restrict__ xr = p.tb.x + static_cast<size_t>(tr.row) * kXStride;
+    const float* __restrict__ wv = p.tb.w + static_cast<size_t>(sv.y) * kWStride;
+    float* ob = p.obs + static_cast<size_t>(e) * kObsDim;
+    // bias first, then the 24 table features, then the three agent terms
+    double zb = static_cast<double>(__ldg(wv + kWOther + 6)), ze = static_cast<double>(__ldg(wv + kWOther + 7));
+    double heat_qi = 0.0;
 #pragma unroll
     for (int u = 0; u < 24; ++u) {
       const double x = __ldg(xr + u);
-      zb = fma(x, static_cast<double>(__ldg(wv + coef_pos_table(u, 0))), zb);
-      ze = fma(x, static_cast<double>(__ldg(wv + coef_pos_table(u, 1))), ze);
+      if (u == 0) heat_qi = x;
+      zb = fma(x, static_cast<double>(__ldg(wv + 2 * u)), zb);
+      ze = fma(x, static_cast<double>(__ldg(wv + 2 * u + 1)), ze);
+      if (!tr.done) ob[slot_of_feature(u)] = static_cast<float>(x);  // obs of day t (Q2)
     }
-    const double other[4] = {static_cast<double>(tr.lag), static_cast<double>(tr.streak),
-                             static_cast<double>(tr.rem), 1.0};
+    const double other[3] = {static_cast<double>(tr.lag), static_cast<double>(tr.streak),
+                             static_cast<double>(tr.rem)};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      zb = fma(other[q], static_cast<double>(__ldg(wv + coef_pos_other(q, 0))), zb);
-      ze = fma(other[q], static_cast<double>(__ldg(wv + coef_pos_other(q, 1))), ze);
+    for (int k = 0; k < 3; ++k) {
+      zb = fma(other[k], static_cast<double>(__ldg(wv + kWOther + 2 * k)), zb);
+      ze = fma(other[k], static_cast<double>(__ldg(wv + kWOther + 2 * k + 1)), ze);
     }
-    const int gate = __ldg(xr) > 0.5;  // heat_qi is table feature 0 (env.py:218; Q4)
-    p.reward[e] = reward_from_logits(zb, ze, gate, tr.act);
+    // reward = -1000/152 * sigmoid(z_b) * (1 - sigmoid(z_e) * [heat_qi > 0.5] * action)  (env.py:211-221)
+    const double baseline = expit(zb);
+    const double eff = (tr.act && heat_qi > 0.5) ? expit(ze) : 0.0;
+    p.reward[e] = static_cast<float>(kRewardScale * baseline * (1.0 - eff));
     p.terminated[e] = static_cast<uint8_t>(tr.done);
     if (p.remaining) p.remaining[e] = tr.rem;
     if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
-
     if (!tr.done) {  // on and after the last day the previous observation stands (Q2)
-      const float* __restrict__ xo = p.tb.xobs + static_cast<size_t>(tr.row) * kXobsStride;
-      float* ob = p.obs + static_cast<size_t>(e) * kObsDim;
-#pragma unroll
-      for (int s = 0; s < kObsDim; ++s) {
-        float v;
-        if (s == 23) v = static_cast<float>(tr.lag);
-        else if (s == 24) v = static_cast<float>(tr.streak);
-        else if (s == 25) v = static_cast<float>(tr.rem);
-        else if (s == 28) v = static_cast<float>(tr.cnt14);
-        else v = __ldg(xo + xobs_pos(s));
-        ob[s] = v;
-      }
+      ob[23] = static_cast<float>(tr.lag);
+      ob[24] = static_cast<float>(tr.streak);
+      ob[25] = static_cast<float>(tr.rem);
+      ob[27] = sig_to_obs(static_cast<float>(__ldg(xr + kXSig)));
+      ob[28] = static_cast<float>(tr.cnt14);
     }
   }
 }
 
 // =========================================================================================
-// step, variant COOP: a warp owns 32 consecutive envs.  Phase A is one thread per env
-// (coalesced state/action traffic, integer transition).  Phase B walks the 32 envs four
-// at a time, 8 lanes per env: every table row is fetched as one contiguous run, the
-// float64 partial dot products are folded inside the 8-lane group with shuffles, and the
-// observation row is written as contiguous 32-byte pieces.  Phase C is one thread per
-// env again (two float64 sigmoids, reward, flags).
+// Lane roles shared by the COOP step kernel and the reset kernel.  Lane q (0..7) of an
+// env's 8-lane group loads record positions {2q, 2q+1} (load A) and {16+2q, 17+2q} (load
+// B) of the day-row and the matching (b,e) coefficient pairs.  Positions 24..31 carry no
+// table feature: B of lanes 4..7 is (sig, 0) / zeros on the x side, zeros (lanes 4,5) or
+// the non-table coefficients (lanes 6,7) on the w side, so their products vanish.  For
+// the observation a lane owns these slots:
+//   A.x -> 2q      A.y -> 2q+1
+//   B.x -> 16+2q (q<4) | 27 significance (q=4) | 23 alert_lag1 (q=5) | 25 remaining_budget (q=6)
+//   B.y -> 17+2q (q<3) | 26 (q=3) | 28 alert_2wks (q=4) | 24 alert_streak (q=5)
+// =========================================================================================
+struct LaneSlots {
+  int bx, by;  // observation slot written from B.x / B.y, -1 = none
+};
+__device__ __forceinline__ LaneSlots lane_slots(int q) {
+  LaneSlots s;
+  s.bx = q < 4 ? 16 + 2 * q : (q == 4 ? 27 : (q == 5 ? 23 : (q == 6 ? 25 : -1)));
+  s.by = q < 3 ? 17 + 2 * q : (q == 3 ? 26 : (q == 4 ? 28 : (q == 5 ? 24 : -1)));
+  return s;
+}
+
+#ifndef W2A_COOP_WARPS
+#define W2A_COOP_WARPS 8  // warps per CTA
+#endif
+#ifndef W2A_COOP_MINBLOCKS
+#define W2A_COOP_MINBLOCKS 3  // CTAs per SM the register allocation is sized for
+#endif
+constexpr int kCoopWarps = W2A_COOP_WARPS;
+
+// per-warp shared memory of the COOP kernel
+struct __align__(16) WarpScratch {
+  double2 part[8][32];      // [round][lane ^ round]: (pb, pe) partial dot products
+  float4 other[4][2][8];    // [group][lane-6][round ^ (2*group + lane-6)]: raw non-table coefficients for the env's owner
+  float obs[32 * kObsDim];  // the warp's 32 observation rows, same layout as in global memory
+};
+constexpr int kCoopSmemBytes = kCoopWarps * static_cast<int>(sizeof(WarpScratch));
+
+struct RoundLoads {
+  double2 xa, xb;
+  float4 wa, wb;
+};
+
+__device__ __forceinline__ RoundLoads issue_round(const double2* x_lane, const float4* w_lane, unsigned row,
+                                                  unsigned cv) {
+  RoundLoads r;
+  const double2* xr = x_lane + static_cast<size_t>(row) * (kXStride / 2);
+  const float4* wr = w_lane + static_cast<size_t>(cv) * (kWStride / 4);
+  r.xa = __ldg(xr);
+  r.xb = __ldg(xr + 8);
+  r.wa = __ldg(wr);
+  r.wb = __ldg(wr + 8);
+  return r;
+}
+
+// =========================================================================================
+// step, variant COOP: a warp owns 32 consecutive envs.
+//
+//   phase A  one thread per env: coalesced state/action traffic and the integer transition.
+//   phase B  eight rounds, four envs per round, 8 lanes per env: four 128-bit loads per
+//            lane fetch the env's day-row and coefficient record (the next round's loads
+//            are issued before this round's math); the lane's float64 partial dot products
+//            and its observation slots go to shared memory.  No branches: the heat_qi gate
+//            is folded into the effectiveness logit as -inf.
+//   phase C  one thread per env: it sums the 8 partials of its env (XOR-swizzled, conflict
+//            free), adds the three agent terms and the bias, evaluates the two float64
+//            sigmoids and writes reward and flags; then the warp streams its 32 staged
+//            observation rows out as one contiguous run.
 // =========================================================================================
 template <int ADT>
-__global__ void __launch_bounds__(256) step_coop_kernel(const StepArgs p) {
+__global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop_kernel(const StepArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int q = lane & 7;
-  const bool hi = (q & 4) != 0;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int n_groups = (p.n + 31) >> 5;
+  const double2* const x_lane = reinterpret_cast<const double2*>(p.tb.x) + q;
+  const float4* const w_lane = reinterpret_cast<const float4*>(p.tb.w) + q;
+  const LaneSlots ls = lane_slots(q);
+  float* const stage_lane = ws.obs + (lane & 24) * kObsDim;  // rows of this lane's 8-env group
+  double2* const part0 = &ws.part[0][lane];
+  // agent counters shown in the observation: B.y of lane 5 = streak, of lane 4 = alert_2wks
+  const int by_shift = q == 5 ? 8 : 16;
+  const int by_mask = q == 5 ? 0xff : 0xf;
+  const int oth_swz = 2 * (lane >> 3) + (q & 1);  // bank swizzle of `other` (lanes 6,7 write it)
 
   for (int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wg < n_groups; wg += warps_total) {
     const int base = wg << 5;
@@ -212,96 +278,121 @@ __global__ void __launch_bounds__(256) step_coop_kernel(const StepArgs p) {
     const bool valid = e < p.n;
     const int ec = valid ? e : p.n - 1;
 
-    // ---- phase A: state transition, one thread per env ----------------------------------
+    // ---- phase A ---------------------------------------------------------------------------
     const uint2 sv = ld_stream(p.st_static + ec);
     uint2 mv = ld_stream(p.st_mut + ec);
     const int a = load_action<ADT>(p.action, ec);
     const Transition tr = advance(sv, mv, a);
     if (valid) st_stream(p.st_mut + e, mv);
-    // lag:1 | skip_obs:1 | streak:8 | cnt14:8 -- what the other lanes need of this env
-    const int packed = tr.lag | ((tr.done || !valid) ? 2 : 0) | (tr.streak << 8) | (tr.cnt14 << 16);
+    const unsigned cv = sv.y;
+    const bool write_obs = valid && !tr.done;  // on and after the last day the previous obs stands (Q2)
+    const int pk = tr.lag | (tr.streak << 8) | (tr.cnt14 << 16);
+    const unsigned wmask = __ballot_sync(kFull, write_obs);
 
-    // ---- phase B: 8 lanes per env ---------------------------------------------------------
-    double zb = 0.0, ze = 0.0;
-    int gate = 0;
+    // ---- phase B ---------------------------------------------------------------------------
+    unsigned rowj = __shfl_sync(kFull, tr.row, 0, 8);
+    unsigned cvj = __shfl_sync(kFull, cv, 0, 8);
+    RoundLoads cur = issue_round(x_lane, w_lane, rowj, cvj);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const unsigned rowj = __shfl_sync(kFull, tr.row, it, 8);
-      const unsigned cvj = __shfl_sync(kFull, sv.y, it, 8);
-      const int pkj = __shfl_sync(kFull, packed, it, 8);
+      const int pkj = __shfl_sync(kFull, pk, it, 8);
       const int remj = __shfl_sync(kFull, tr.rem, it, 8);
-
-      const double* __restrict__ xr = p.tb.xrew + static_cast<size_t>(rowj) * kXrewStride;
-      const double2 x01 = __ldg(reinterpret_cast<const double2*>(xr) + q);  // features 2q, 2q+1
-      const double x2 = __ldg(xr + 16 + q);                                 // feature 16+q
-      const float4* __restrict__ wv =
-          reinterpret_cast<const float4*>(p.tb.w + static_cast<size_t>(cvj) * kCoefStride);
-      const float4 w0 = __ldg(wv + q);      // (b,e) of feature 2q, (b,e) of feature 2q+1
-      const float4 w1 = __ldg(wv + 8 + q);  // (b,e) of feature 16+q, (b,e) of this lane's other term
-      const float4 xo =
-          __ldg(reinterpret_cast<const float4*>(p.tb.xobs + static_cast<size_t>(rowj) * kXobsStride) + q);
-
-      const int lagj = pkj & 1;
-      const int streakj = (pkj >> 8) & 0xff;
-      // the term that does not come from the table: lag1 / streak / remaining / bias / none
-      const double xoth = q == 0 ? static_cast<double>(lagj)
-                        : q == 1 ? static_cast<double>(streakj)
-                        : q == 2 ? static_cast<double>(remj)
-                        : q == 3 ? 1.0 : 0.0;
-      double pb = x01.x * static_cast<double>(w0.x);
-      double pe = x01.x * static_cast<double>(w0.y);
-      pb = fma(x01.y, static_cast<double>(w0.z), pb);
-      pe = fma(x01.y, static_cast<double>(w0.w), pe);
-      pb = fma(x2, static_cast<double>(w1.x), pb);
-      pe = fma(x2, static_cast<double>(w1.y), pe);
-      pb = fma(xoth, static_cast<double>(w1.z), pb);
-      pe = fma(xoth, static_cast<double>(w1.w), pe);
-      const int g0 = (q == 0) && (x01.x > 0.5);  // heat_qi gate lives in lane 0 (Q4)
-
-      // fold 8 lanes x 2 heads: lanes 0-3 end with z_b, lanes 4-7 with z_e
-      double v = (hi ? pe : pb) + __shfl_xor_sync(kFull, hi ? pb : pe, 4);
-      v += __shfl_xor_sync(kFull, v, 2);
-      v += __shfl_xor_sync(kFull, v, 1);
-      const double o = __shfl_xor_sync(kFull, v, 4);
-      const int gj = __shfl_sync(kFull, g0, 0, 8);
-      if (q == it) {
-        zb = hi ? o : v;
-        ze = hi ? v : o;
-        gate = gj;
+      RoundLoads nxt;
+      if (it < 7) {
+        rowj = __shfl_sync(kFull, tr.row, it + 1, 8);
+        cvj = __shfl_sync(kFull, cv, it + 1, 8);
+        nxt = issue_round(x_lane, w_lane, rowj, cvj);
       }
+      double pb = cur.xa.x * static_cast<double>(cur.wa.x);
+      double pe = cur.xa.x * static_cast<double>(cur.wa.y);
+      pb = fma(cur.xa.y, static_cast<double>(cur.wa.z), pb);
+      pe = fma(cur.xa.y, static_cast<double>(cur.wa.w), pe);
+      pb = fma(cur.xb.x, static_cast<double>(cur.wb.x), pb);
+      pe = fma(cur.xb.x, static_cast<double>(cur.wb.y), pe);
+      pb = fma(cur.xb.y, static_cast<double>(cur.wb.z), pb);
+      pe = fma(cur.xb.y, static_cast<double>(cur.wb.w), pe);
+      // effectiveness counts only when heat_qi > 0.5 (env.py:218; Q4): heat_qi is lane 0's
+      // A.x; -inf makes sigmoid(z_e) exactly 0
+      if (q == 0 && !(cur.xa.x > 0.5)) pe = -CUDART_INF;
+      part0[it * 32 + ((lane ^ it) - lane)] = make_double2(pb, pe);
+      if (q >= 6) ws.other[lane >> 3][q - 6][it ^ oth_swz] = cur.wb;
 
-      if (!(pkj & 2)) {  // observation of day t (Q2): table row + the four agent slots
-        float v2 = xo.z, v3 = xo.w;
-        if (q == 7) v2 = static_cast<float>(lagj);                  // slot 23 alert_lag1
-        if (q == 0) v3 = static_cast<float>(streakj);               // slot 24 alert_streak
-        if (q == 1) v3 = static_cast<float>(remj);                  // slot 25 remaining_budget
-        if (q == 4) v3 = static_cast<float>((pkj >> 16) & 0xff);    // slot 28 alert_2wks
-        float* ob = p.obs + static_cast<size_t>(base + (lane & 24) + it) * kObsDim + q;
-        st_stream(ob, xo.x);
-        st_stream(ob + 8, xo.y);
-        st_stream(ob + 16, v2);
-        if (q <= 4) st_stream(ob + 24, v3);
+      // observation of day t (Q2): float32 of the table row + the four agent slots
+      float* const st = stage_lane + it * kObsDim;
+      float vbx = static_cast<float>(cur.xb.x), vby = static_cast<float>(cur.xb.y);
+      if (q == 4) vbx = sig_to_obs(vbx);
+      if (q == 5) vbx = static_cast<float>(pkj & 1);
+      if (q == 6) vbx = static_cast<float>(remj);
+      if (q == 4 || q == 5) vby = static_cast<float>((pkj >> by_shift) & by_mask);
+      st[2 * q] = static_cast<float>(cur.xa.x);
+      st[2 * q + 1] = static_cast<float>(cur.xa.y);
+      if (ls.bx >= 0) st[ls.bx] = vbx;
+      if (ls.by >= 0) st[ls.by] = vby;
+      if (it < 7) cur = nxt;
+    }
+    __syncwarp();
+
+    // ---- phase C ---------------------------------------------------------------------------
+    // env (lane) was round q of its 8-lane group; its partials sit in part[q][(g*8+j)^q]
+    {
+      const int g = lane >> 3;
+      const float4 o0 = ws.other[g][0][q ^ (2 * g)];      // (b,e) of alert_lag1, alert_streak
+      const float4 o1 = ws.other[g][1][q ^ (2 * g + 1)];  // (b,e) of remaining_budget, bias
+      double zb = static_cast<double>(o1.z), ze = static_cast<double>(o1.w);
+      const double f_lag = static_cast<double>(tr.lag), f_streak = static_cast<double>(tr.streak),
+                   f_rem = static_cast<double>(tr.rem);
+      zb = fma(f_lag, static_cast<double>(o0.x), zb);
+      ze = fma(f_lag, static_cast<double>(o0.y), ze);
+      zb = fma(f_streak, static_cast<double>(o0.z), zb);
+      ze = fma(f_streak, static_cast<double>(o0.w), ze);
+      zb = fma(f_rem, static_cast<double>(o1.x), zb);
+      ze = fma(f_rem, static_cast<double>(o1.y), ze);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double2 v = ws.part[q][(lane & 24) | (j ^ q)];
+        zb += v.x;
+        ze += v.y;
+      }
+      if (valid) {
+        // reward = -1000/152 * sigmoid(z_b) * (1 - sigmoid(z_e) * [heat_qi > 0.5] * action)  (env.py:211-221)
+        const double baseline = expit(zb);
+        const double eff = tr.act ? expit(ze) : 0.0;
+        __stcs(p.reward + e, static_cast<float>(kRewardScale * baseline * (1.0 - eff)));
+        p.terminated[e] = static_cast<uint8_t>(tr.done);
+        if (p.remaining) __stcs(p.remaining + e, tr.rem);
+        if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
       }
     }
-
-    // ---- phase C: reward and flags, one thread per env --------------------------------------
-    if (valid) {
-      __stcs(p.reward + e, reward_from_logits(zb, ze, gate, tr.act));
-      p.terminated[e] = static_cast<uint8_t>(tr.done);
-      if (p.remaining) __stcs(p.remaining + e, tr.rem);
-      if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
+    // observation rows: 32 x 116 B contiguous in global memory (base is a multiple of 32)
+    float* const ob = p.obs + static_cast<size_t>(base) * kObsDim;
+    if (wmask == kFull && ((reinterpret_cast<uintptr_t>(p.obs) & 15) == 0)) {
+      const float4* src = reinterpret_cast<const float4*>(ws.obs);
+      float4* dst = reinterpret_cast<float4*>(ob);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = k * 32 + lane;
+        if (i < 32 * kObsDim / 4) __stcs(dst + i, src[i]);
+      }
+    } else if (wmask != 0u) {  // ragged tail or some envs already on their last day
+      for (int i = lane; i < 32 * kObsDim; i += 32) {
+        const int env = (i * 565) >> 14;  // i / 29 for i < 928
+        if ((wmask >> env) & 1u) st_stream(ob + i, ws.obs[i]);
+      }
     }
+    __syncwarp();
   }
 }
 
 // =========================================================================================
 // reset: host index streams -> state + first observation (env.py:155-184).
-// Same warp shape as the COOP step: thread per env for the state, 8 lanes per env for
-// the observation row.
+// Same warp shape and lane roles as the COOP step; observations go straight to global
+// memory (a reset happens once per 153 steps).
 // =========================================================================================
 __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
   const int lane = threadIdx.x & 31;
   const int q = lane & 7;
+  const LaneSlots ls = lane_slots(q);
+  const double2* const x_lane = reinterpret_cast<const double2*>(p.tb.x) + q;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int n_groups = (p.n + 31) >> 5;
   for (int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wg < n_groups; wg += warps_total) {
@@ -329,18 +420,18 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
       const int budj = __shfl_sync(kFull, budget, it, 8);
       const int takej = __shfl_sync(kFull, static_cast<int>(take), it, 8);
       if (takej) {
-        const float4 xo =
-            __ldg(reinterpret_cast<const float4*>(p.tb.xobs + static_cast<size_t>(rowj) * kXobsStride) + q);
-        float v2 = xo.z, v3 = xo.w;
-        if (q == 7) v2 = 0.f;                          // alert_lag1 (t == 0)
-        if (q == 0) v3 = 0.f;                          // alert_streak
-        if (q == 1) v3 = static_cast<float>(budj);     // remaining_budget = budget
-        if (q == 4) v3 = 0.f;                          // alert_2wks
-        float* ob = p.obs + static_cast<size_t>(base + (lane & 24) + it) * kObsDim + q;
-        st_stream(ob, xo.x);
-        st_stream(ob + 8, xo.y);
-        st_stream(ob + 16, v2);
-        if (q <= 4) st_stream(ob + 24, v3);
+        const double2* xr = x_lane + static_cast<size_t>(rowj) * (kXStride / 2);
+        const double2 xa = __ldg(xr), xb = __ldg(xr + 8);
+        float vbx = static_cast<float>(xb.x), vby = static_cast<float>(xb.y);
+        if (q == 4) vbx = sig_to_obs(vbx);
+        if (q == 5) vbx = 0.f;                        // alert_lag1 (t == 0)
+        if (q == 6) vbx = static_cast<float>(budj);   // remaining_budget = budget
+        if (q == 4 || q == 5) vby = 0.f;              // alert_2wks, alert_streak
+        float* ob = p.obs + static_cast<size_t>(base + (lane & 24) + it) * kObsDim;
+        st_stream(ob + 2 * q, static_cast<float>(xa.x));
+        st_stream(ob + 2 * q + 1, static_cast<float>(xa.y));
+        if (ls.bx >= 0) st_stream(ob + ls.bx, vbx);
+        if (ls.by >= 0) st_stream(ob + ls.by, vby);
       }
     }
   }

@@ -17,24 +17,20 @@ import numpy as np
 
 from . import schema
 
-XREW_STRIDE = 24
-XOBS_STRIDE = 32
-COEF_STRIDE = 64
+X_STRIDE = 32  # float64 per day-row record
+W_STRIDE = 64  # float32 per coefficient record
+X_SIG = 24  # record position of the significance code
+W_OTHER = 56  # first float of the non-table coefficients (lag1, streak, remaining, bias)
 
 
 def coef_pos_table(u: int, head: int) -> int:
-    """Float offset of (table feature `u`, head) in a packed coefficient vector."""
-    return 2 * u + head if u < 16 else 32 + 4 * (u - 16) + head
+    """Float offset of (table feature `u`, head) in a coefficient record."""
+    return 2 * u + head
 
 
-def coef_pos_other(q: int, head: int) -> int:
-    """Float offset of lane `q`'s non-table term (0 lag1, 1 streak, 2 remaining, 3 bias)."""
-    return 32 + 4 * q + 2 + head
-
-
-def xobs_pos(slot: int) -> int:
-    """Float offset of observation slot `slot` in a packed observation row."""
-    return 4 * (slot & 7) + (slot >> 3)
+def coef_pos_other(k: int, head: int) -> int:
+    """Float offset of non-table term `k` (0 lag1, 1 streak, 2 remaining, 3 bias)."""
+    return W_OTHER + 2 * k + head
 
 
 #: coefficient slot (0..26 feature, 27 bias) -> float offset of its baseline coefficient
@@ -45,7 +41,6 @@ _COEF_POS[schema.SLOT_ALERT_LAG1] = coef_pos_other(0, 0)
 _COEF_POS[schema.SLOT_ALERT_STREAK] = coef_pos_other(1, 0)
 _COEF_POS[schema.SLOT_REMAINING_BUDGET] = coef_pos_other(2, 0)
 _COEF_POS[27] = coef_pos_other(3, 0)
-_XOBS_POS = np.array([xobs_pos(s) for s in range(28)], dtype=np.int64)
 
 
 @dataclass
@@ -80,19 +75,14 @@ class FeatureStore:
         return self.feat[:, :, 0, schema.SLOT_REMAINING_BUDGET].astype(np.int32)
 
     # ---- packing for the device -----------------------------------------------------
-    def pack_xrew(self) -> np.ndarray:
-        """float64 [S*Y*T, 24]: the reward features that are read from the table."""
+    def pack_x(self) -> np.ndarray:
+        """float64 [S*Y*T, 32] day-row records: positions 0..23 the reward features that are
+        read from the table (obs slots 0..22 and 26), 24 the significance code with 0.0 for
+        "none" (the kernels show it as NaN), 25..31 zero."""
         S, Y, T = self.shape
-        return np.ascontiguousarray(
-            self.feat[..., list(schema.TABLE_REWARD_SLOTS)].reshape(S * Y * T, XREW_STRIDE)
-        )
-
-    def pack_xobs(self) -> np.ndarray:
-        """float32 [S*Y*T, 32]: observation slots 0..27, lane-permuted (float 4q+i = slot 8i+q)."""
-        S, Y, T = self.shape
-        out = np.zeros((S * Y * T, XOBS_STRIDE), dtype=np.float32)
-        out[:, _XOBS_POS[:27]] = self.feat.reshape(S * Y * T, 27).astype(np.float32)
-        out[:, _XOBS_POS[27]] = self.sig_code.reshape(-1)
+        out = np.zeros((S * Y * T, X_STRIDE), dtype=np.float64)
+        out[:, :24] = self.feat[..., list(schema.TABLE_REWARD_SLOTS)].reshape(S * Y * T, 24)
+        out[:, X_SIG] = np.nan_to_num(self.sig_code.reshape(-1).astype(np.float64), nan=0.0)
         return out
 
     # ---- constructors -----------------------------------------------------------------
@@ -173,13 +163,14 @@ class RewardWeights:
         return self.coef.shape[0]
 
     def pack(self) -> np.ndarray:
-        """float32 [S*P, 64]: vector ``col*P + p``, lane-permuted (see `coef_pos_*`)."""
+        """float32 [S*P, 64] coefficient records: record ``col*P + p`` = 24 table features x
+        (b,e), 8 zeros, then the four non-table terms x (b,e) (see `coef_pos_*`)."""
         P, S = self.coef.shape[:2]
-        out = np.zeros((S, P, COEF_STRIDE), dtype=np.float32)
+        out = np.zeros((S, P, W_STRIDE), dtype=np.float32)
         c = np.transpose(self.coef, (1, 0, 2, 3))  # [S, P, 2, 28]
         out[:, :, _COEF_POS] = c[:, :, 0, :]
         out[:, :, _COEF_POS + 1] = c[:, :, 1, :]
-        return out.reshape(S * P, COEF_STRIDE)
+        return out.reshape(S * P, W_STRIDE)
 
     @classmethod
     def from_tensors(cls, tensors: dict, fips_list: Sequence) -> "RewardWeights":
