@@ -41,7 +41,7 @@ extern "C" {
 #define W2A_OBS_DIM 29
 /* Device table records (see DESIGN.md "Data layout in HBM"): both are 256 bytes, and the
  * tables must be 128-byte aligned so that a record is exactly two cache lines. */
-#define W2A_X_STRIDE 32 /* float64 per day-row: 0..23 table reward features, 24 significance code, 25..31 zero */
+#define W2A_X_STRIDE 32 /* float64 per day-row: 0..23 table reward features, 24 significance code, 25 gate, 26..31 zero */
 #define W2A_W_STRIDE 64 /* float32 per (county, posterior sample): (baseline, effectiveness) pairs */
 
 /* action_dtype */
@@ -75,7 +75,8 @@ int w2a_destroy(w2a_ctx* ctx);
  *                                    the reward features read from the table (observation slots
  *                                    0..22 and 26, float64 as in the parquet files), position 24
  *                                    the significance code (0.0 = none, shown as NaN; k = label
- *                                    k), positions 25..31 must be 0.0
+ *                                    k), position 25 the heat_qi gate (0.0 if heat_qi > 0.5 else
+ *                                    -1e300; env.py:218), positions 26..31 must be 0.0
  *   n_days  dev uint8   [S*Y]        days in episode (county, year); 0 = no such episode
  *   budget0 dev int32   [S*Y]        historical `remaining_budget` of day 0 (env.py:169)
  * The tables are referenced, not copied, and must outlive their use.  S*Y*T < 2^24. */
@@ -86,8 +87,8 @@ int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const
  * `self.effectiveness_coefs`, env.py:77-82).
  *   w  dev float32 [S_w*P, 64]; record (col*P + p) holds the coefficients of county column
  *      `col`, posterior sample `p` as (baseline, effectiveness) pairs: floats 0..47 the 24
- *      table features in record order, 48..55 must be 0, 56..63 alert_lag1, alert_streak,
- *      remaining_budget, bias. */
+ *      table features in record order, 48..55 must be 0 except float 51 = 1.0 (effectiveness
+ *      coefficient of the gate column), 56..63 alert_lag1, alert_streak, remaining_budget, bias. */
 int w2a_set_coefs(w2a_ctx* ctx, const float* w, int P, int S_w);
 
 /* Bytes of the opaque per-env state for `n` envs (16 bytes per env, two SoA planes). */

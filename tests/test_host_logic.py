@@ -29,7 +29,9 @@ def test_pack_layouts_round_trip(golden):
         np.testing.assert_array_equal(x[..., u], store.feat[..., slot])
     sig = x[..., X_SIG]
     np.testing.assert_array_equal(np.where(sig == 0, np.nan, sig).astype(np.float32), store.sig_code)
-    assert (x[..., 25:] == 0).all() and np.isfinite(x).all()
+    heat_qi = store.feat[..., 0]
+    np.testing.assert_array_equal(x[..., 25], np.where(heat_qi > 0.5, 0.0, -1e300))
+    assert (x[..., 26:] == 0).all() and np.isfinite(x).all()
     packed = w.pack().reshape(len(w.fips_list), w.n_samples, W_STRIDE)
     seen = set()
     for h in (0, 1):
@@ -39,7 +41,8 @@ def test_pack_layouts_round_trip(golden):
         for k, slot in enumerate((23, 24, 25, 27)):
             np.testing.assert_array_equal(packed[:, :, coef_pos_other(k, h)], w.coef[:, :, h, slot].T)
             seen.add(coef_pos_other(k, h))
-    assert len(seen) == 56 and all((packed[..., p] == 0).all() for p in range(W_STRIDE) if p not in seen)
+    assert (packed[..., 51] == 1.0).all()  # effectiveness coefficient of the gate column
+    assert len(seen) == 56 and all((packed[..., p] == 0).all() for p in range(W_STRIDE) if p not in seen and p != 51)
     assert seen == set(range(48)) | set(range(56, 64))
 
 

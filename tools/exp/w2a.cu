@@ -1,0 +1,410 @@
+// w2a.cu -- C ABI (include/w2a.h) over the sm_100a kernels in w2a_kernels.cuh.
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+//        -Xcompiler -fPIC -shared -I include -o weather2alert_b200/libw2a.so w2a.cu
+#include "w2a.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "w2a_kernels.cuh"
+
+namespace {
+
+constexpr int kHostStreams = 3;
+constexpr int64_t kHostChunk = 1 << 16;  // envs per pipelined chunk of the *_host calls
+
+struct HostEnvs {
+  int64_t n = 0;
+  void* state = nullptr;
+  uint8_t* action = nullptr;
+  float* obs = nullptr;
+  float* reward = nullptr;
+  uint8_t* terminated = nullptr;
+  int32_t* remaining = nullptr;
+  uint8_t* at_budget = nullptr;
+  int32_t* idx = nullptr;  // 5 planes of n int32: loc, year, coef_col, coef_idx, budget
+  uint8_t* mask = nullptr;
+  cudaStream_t streams[kHostStreams] = {};
+};
+
+char g_create_error[512] = "";
+constexpr int kMaxKernels = 16;
+
+}  // namespace
+
+struct w2a_ctx {
+  int device = 0;
+  int sm_count = 0;
+  w2a::Tables tb = {};
+  bool have_features = false;
+  bool have_coefs = false;
+  int64_t launches = 0;
+  HostEnvs* host = nullptr;
+  const void* occ_key[kMaxKernels] = {};  // occupancy (CTAs per SM) of each kernel launched so far
+  int occ_val[kMaxKernels] = {};
+  int n_occ = 0;
+  char err[512] = "";
+};
+
+namespace {
+
+int fail(w2a_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_create_error;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define W2A_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t err__ = (expr);                                                          \
+    if (err__ != cudaSuccess)                                                            \
+      return fail((ctx), W2A_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(err__)); \
+  } while (0)
+
+// Persistent-style grid: enough CTAs to fill every SM at the kernel's occupancy, never
+// more than the work needs; the kernels walk the envs with a grid-stride loop.
+template <typename K>
+int grid_for(w2a_ctx* ctx, K kernel, int block, size_t smem, int64_t work_items_per_block, int64_t n, int* grid) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  int per_sm = 0;
+  for (int i = 0; i < ctx->n_occ; ++i)
+    if (ctx->occ_key[i] == key) per_sm = ctx->occ_val[i];
+  if (per_sm == 0) {  // asked once per kernel and context
+    if (smem > 48 * 1024)
+      W2A_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    W2A_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+    if (per_sm < 1) return fail(ctx, W2A_E_CUDA, "kernel does not fit on an SM (block %d, %zu B shared)", block, smem);
+    if (ctx->n_occ < kMaxKernels) {
+      ctx->occ_key[ctx->n_occ] = key;
+      ctx->occ_val[ctx->n_occ++] = per_sm;
+    }
+  }
+  const int64_t need = (n + work_items_per_block - 1) / work_items_per_block;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
+  *grid = static_cast<int>(std::max<int64_t>(1, std::min(need, cap)));
+  return W2A_OK;
+}
+
+template <int ADT>
+int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int variant) {
+  int grid = 0;
+  if (variant == W2A_STEP_THREAD) {
+    int rc = grid_for(ctx, w2a::step_thread_kernel<ADT>, 128, 0, 128, a.n, &grid);
+    if (rc) return rc;
+    w2a::step_thread_kernel<ADT><<<grid, 128, 0, st>>>(a);
+  } else {
+    constexpr int kBlock = 32 * w2a::kCoopWarps;
+    int rc = grid_for(ctx, w2a::step_coop_kernel<ADT>, kBlock, w2a::kCoopSmemBytes, kBlock, a.n, &grid);
+    if (rc) return rc;
+    w2a::step_coop_kernel<ADT><<<grid, kBlock, w2a::kCoopSmemBytes, st>>>(a);
+  }
+  ctx->launches++;
+  W2A_CUDA(ctx, cudaGetLastError());
+  return W2A_OK;
+}
+
+int step_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const void* action, int action_dtype,
+                const uint2* st_static, uint2* st_mut, float* obs, float* reward,
+                uint8_t* terminated, int32_t* remaining, uint8_t* at_budget, int variant) {
+  if (variant == W2A_STEP_AUTO) variant = n < 32768 ? W2A_STEP_THREAD : W2A_STEP_COOP;
+  if (variant != W2A_STEP_THREAD && variant != W2A_STEP_COOP)
+    return fail(ctx, W2A_E_INVALID, "w2a_step: unknown variant %d", variant);
+  w2a::StepArgs a;
+  a.tb = ctx->tb;
+  a.st_static = st_static;
+  a.st_mut = st_mut;
+  a.action = action;
+  a.obs = obs;
+  a.reward = reward;
+  a.terminated = terminated;
+  a.remaining = remaining;
+  a.at_budget = at_budget;
+  a.n = static_cast<int>(n);
+  switch (action_dtype) {
+    case W2A_ACT_U8: return launch_step<0>(ctx, st, a, variant);
+    case W2A_ACT_I32: return launch_step<1>(ctx, st, a, variant);
+    case W2A_ACT_I64: return launch_step<2>(ctx, st, a, variant);
+    default: return fail(ctx, W2A_E_INVALID, "w2a_step: unknown action_dtype %d", action_dtype);
+  }
+}
+
+int reset_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const int32_t* loc, const int32_t* year,
+                 const int32_t* coef_col, const int32_t* coef_idx, const int32_t* budget,
+                 const uint8_t* mask, uint2* st_static, uint2* st_mut, float* obs,
+                 int32_t* remaining) {
+  w2a::ResetArgs a;
+  a.tb = ctx->tb;
+  a.loc = loc;
+  a.year = year;
+  a.coef_col = coef_col;
+  a.coef_idx = coef_idx;
+  a.budget = budget;
+  a.mask = mask;
+  a.st_static = st_static;
+  a.st_mut = st_mut;
+  a.obs = obs;
+  a.remaining = remaining;
+  a.n = static_cast<int>(n);
+  int grid = 0;
+  int rc = grid_for(ctx, w2a::reset_kernel, 256, 0, 256, n, &grid);
+  if (rc) return rc;
+  w2a::reset_kernel<<<grid, 256, 0, st>>>(a);
+  ctx->launches++;
+  W2A_CUDA(ctx, cudaGetLastError());
+  return W2A_OK;
+}
+
+int check_ready(w2a_ctx* ctx, const char* who, int64_t n) {
+  if (!ctx) return W2A_E_INVALID;
+  if (!ctx->have_features || !ctx->have_coefs)
+    return fail(ctx, W2A_E_NOTREADY, "%s: call w2a_set_features and w2a_set_coefs first", who);
+  if (n < 0 || n >= (int64_t{1} << 31) - 64)
+    return fail(ctx, W2A_E_INVALID, "%s: n=%lld out of range", who, static_cast<long long>(n));
+  return W2A_OK;
+}
+
+inline uint2* plane_static(void* state) { return reinterpret_cast<uint2*>(state); }
+inline uint2* plane_mut(void* state, int64_t n) { return reinterpret_cast<uint2*>(state) + n; }
+
+}  // namespace
+
+extern "C" {
+
+int w2a_version(void) { return W2A_VERSION; }
+
+const char* w2a_last_error(const w2a_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int w2a_create(int device, w2a_ctx** out) {
+  if (!out) return fail(nullptr, W2A_E_INVALID, "w2a_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess)
+    return fail(nullptr, W2A_E_CUDA, "w2a_create: cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    return fail(nullptr, W2A_E_INVALID, "w2a_create: device %d not in [0,%d)", device, count);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess)
+    return fail(nullptr, W2A_E_CUDA, "w2a_create: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, W2A_E_INVALID,
+                "w2a_create: device %d is sm_%d%d; this library carries sm_100a code only", device,
+                prop.major, prop.minor);
+  w2a_ctx* ctx = new (std::nothrow) w2a_ctx();
+  if (!ctx) return fail(nullptr, W2A_E_NOMEM, "w2a_create: out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return W2A_OK;
+}
+
+int w2a_destroy(w2a_ctx* ctx) {
+  if (!ctx) return W2A_OK;
+  w2a_host_envs_destroy(ctx);
+  delete ctx;
+  return W2A_OK;
+}
+
+int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const int32_t* budget0, int S, int Y,
+                     int T) {
+  if (!ctx) return W2A_E_INVALID;
+  if (!x || !n_days || !budget0) return fail(ctx, W2A_E_INVALID, "w2a_set_features: NULL table");
+  if (S <= 0 || Y <= 0 || T <= 0 || T > 255)
+    return fail(ctx, W2A_E_INVALID, "w2a_set_features: bad shape S=%d Y=%d T=%d (T<=255)", S, Y, T);
+  if (static_cast<int64_t>(S) * Y * T >= (int64_t{1} << 24))
+    return fail(ctx, W2A_E_INVALID, "w2a_set_features: S*Y*T=%lld rows exceed the 24-bit row index",
+                static_cast<long long>(static_cast<int64_t>(S) * Y * T));
+  if (reinterpret_cast<uintptr_t>(x) & 127)
+    return fail(ctx, W2A_E_INVALID, "w2a_set_features: the table must be 128-byte aligned");
+  ctx->tb.x = x;
+  ctx->tb.n_days = n_days;
+  ctx->tb.budget0 = budget0;
+  ctx->tb.S = S;
+  ctx->tb.Y = Y;
+  ctx->tb.T = T;
+  ctx->have_features = true;
+  return W2A_OK;
+}
+
+int w2a_set_coefs(w2a_ctx* ctx, const float* w, int P, int S_w) {
+  if (!ctx) return W2A_E_INVALID;
+  if (!w || P <= 0 || S_w <= 0) return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: bad argument");
+  if (reinterpret_cast<uintptr_t>(w) & 127)
+    return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: the table must be 128-byte aligned");
+  if (static_cast<int64_t>(P) * S_w >= (int64_t{1} << 31))
+    return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: P*S_w too large");
+  ctx->tb.w = w;
+  ctx->tb.P = P;
+  ctx->tb.Sw = S_w;
+  ctx->have_coefs = true;
+  return W2A_OK;
+}
+
+size_t w2a_state_bytes(int64_t n) { return n < 0 ? 0 : static_cast<size_t>(n) * 16; }
+
+int w2a_reset(w2a_ctx* ctx, void* stream, int64_t n, const int32_t* loc, const int32_t* year,
+              const int32_t* coef_col, const int32_t* coef_idx, const int32_t* budget,
+              const uint8_t* mask, void* state, float* obs, int32_t* remaining) {
+  int rc = check_ready(ctx, "w2a_reset", n);
+  if (rc) return rc;
+  if (n == 0) return W2A_OK;
+  if (!loc || !year || !coef_col || !coef_idx || !state || !obs)
+    return fail(ctx, W2A_E_INVALID, "w2a_reset: NULL argument");
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  return reset_planes(ctx, static_cast<cudaStream_t>(stream), n, loc, year, coef_col, coef_idx, budget,
+                      mask, plane_static(state), plane_mut(state, n), obs, remaining);
+}
+
+int w2a_step(w2a_ctx* ctx, void* stream, int64_t n, const void* action, int action_dtype, void* state,
+             float* obs, float* reward, uint8_t* terminated, int32_t* remaining, uint8_t* at_budget,
+             int variant) {
+  int rc = check_ready(ctx, "w2a_step", n);
+  if (rc) return rc;
+  if (n == 0) return W2A_OK;
+  if (!action || !state || !obs || !reward || !terminated)
+    return fail(ctx, W2A_E_INVALID, "w2a_step: NULL argument");
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  return step_planes(ctx, static_cast<cudaStream_t>(stream), n, action, action_dtype, plane_static(state),
+                     plane_mut(state, n), obs, reward, terminated, remaining, at_budget, variant);
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------
+
+int w2a_host_envs_destroy(w2a_ctx* ctx) {
+  if (!ctx || !ctx->host) return W2A_OK;
+  HostEnvs* h = ctx->host;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  cudaFree(h->state);
+  cudaFree(h->action);
+  cudaFree(h->obs);
+  cudaFree(h->reward);
+  cudaFree(h->terminated);
+  cudaFree(h->remaining);
+  cudaFree(h->at_budget);
+  cudaFree(h->idx);
+  cudaFree(h->mask);
+  for (auto& s : h->streams)
+    if (s) cudaStreamDestroy(s);
+  delete h;
+  ctx->host = nullptr;
+  return W2A_OK;
+}
+
+int w2a_host_envs_create(w2a_ctx* ctx, int64_t n) {
+  int rc = check_ready(ctx, "w2a_host_envs_create", n);
+  if (rc) return rc;
+  if (n <= 0) return fail(ctx, W2A_E_INVALID, "w2a_host_envs_create: n must be positive");
+  w2a_host_envs_destroy(ctx);
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  HostEnvs* h = new (std::nothrow) HostEnvs();
+  if (!h) return fail(ctx, W2A_E_NOMEM, "w2a_host_envs_create: out of host memory");
+  ctx->host = h;
+  h->n = n;
+  const size_t un = static_cast<size_t>(n);
+  W2A_CUDA(ctx, cudaMalloc(&h->state, w2a_state_bytes(n)));
+  W2A_CUDA(ctx, cudaMalloc(&h->action, un));
+  W2A_CUDA(ctx, cudaMalloc(&h->obs, un * W2A_OBS_DIM * sizeof(float)));
+  W2A_CUDA(ctx, cudaMalloc(&h->reward, un * sizeof(float)));
+  W2A_CUDA(ctx, cudaMalloc(&h->terminated, un));
+  W2A_CUDA(ctx, cudaMalloc(&h->remaining, un * sizeof(int32_t)));
+  W2A_CUDA(ctx, cudaMalloc(&h->at_budget, un));
+  W2A_CUDA(ctx, cudaMalloc(&h->idx, un * 5 * sizeof(int32_t)));
+  W2A_CUDA(ctx, cudaMalloc(&h->mask, un));
+  W2A_CUDA(ctx, cudaMemset(h->obs, 0, un * W2A_OBS_DIM * sizeof(float)));
+  for (auto& s : h->streams) W2A_CUDA(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  return W2A_OK;
+}
+
+int w2a_reset_host(w2a_ctx* ctx, const int32_t* loc, const int32_t* year, const int32_t* coef_col,
+                   const int32_t* coef_idx, const int32_t* budget, const uint8_t* mask, float* obs,
+                   int32_t* remaining) {
+  if (!ctx) return W2A_E_INVALID;
+  HostEnvs* h = ctx->host;
+  if (!h) return fail(ctx, W2A_E_NOTREADY, "w2a_reset_host: call w2a_host_envs_create first");
+  if (!loc || !year || !coef_col || !coef_idx || !obs)
+    return fail(ctx, W2A_E_INVALID, "w2a_reset_host: NULL argument");
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = h->n;
+  uint2* sstat = plane_static(h->state);
+  uint2* smut = plane_mut(h->state, n);
+  int ci = 0;
+  for (int64_t c0 = 0; c0 < n; c0 += kHostChunk, ++ci) {
+    const int64_t m = std::min(kHostChunk, n - c0);
+    const size_t um = static_cast<size_t>(m);
+    cudaStream_t st = h->streams[ci % kHostStreams];
+    int32_t* d_loc = h->idx + c0;
+    int32_t* d_year = h->idx + n + c0;
+    int32_t* d_col = h->idx + 2 * n + c0;
+    int32_t* d_ci = h->idx + 3 * n + c0;
+    int32_t* d_bud = budget ? h->idx + 4 * n + c0 : nullptr;
+    uint8_t* d_mask = mask ? h->mask + c0 : nullptr;
+    W2A_CUDA(ctx, cudaMemcpyAsync(d_loc, loc + c0, um * 4, cudaMemcpyHostToDevice, st));
+    W2A_CUDA(ctx, cudaMemcpyAsync(d_year, year + c0, um * 4, cudaMemcpyHostToDevice, st));
+    W2A_CUDA(ctx, cudaMemcpyAsync(d_col, coef_col + c0, um * 4, cudaMemcpyHostToDevice, st));
+    W2A_CUDA(ctx, cudaMemcpyAsync(d_ci, coef_idx + c0, um * 4, cudaMemcpyHostToDevice, st));
+    if (budget) W2A_CUDA(ctx, cudaMemcpyAsync(d_bud, budget + c0, um * 4, cudaMemcpyHostToDevice, st));
+    if (mask) W2A_CUDA(ctx, cudaMemcpyAsync(d_mask, mask + c0, um, cudaMemcpyHostToDevice, st));
+    int rc = reset_planes(ctx, st, m, d_loc, d_year, d_col, d_ci, d_bud, d_mask, sstat + c0, smut + c0,
+                          h->obs + c0 * W2A_OBS_DIM, h->remaining + c0);
+    if (rc) return rc;
+    W2A_CUDA(ctx, cudaMemcpyAsync(obs + c0 * W2A_OBS_DIM, h->obs + c0 * W2A_OBS_DIM,
+                                  um * W2A_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (remaining)
+      W2A_CUDA(ctx, cudaMemcpyAsync(remaining + c0, h->remaining + c0, um * 4, cudaMemcpyDeviceToHost, st));
+  }
+  for (auto& s : h->streams) W2A_CUDA(ctx, cudaStreamSynchronize(s));
+  return W2A_OK;
+}
+
+int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward, uint8_t* terminated,
+                  int32_t* remaining, uint8_t* at_budget) {
+  if (!ctx) return W2A_E_INVALID;
+  HostEnvs* h = ctx->host;
+  if (!h) return fail(ctx, W2A_E_NOTREADY, "w2a_step_host: call w2a_host_envs_create first");
+  if (!action || !obs || !reward || !terminated)
+    return fail(ctx, W2A_E_INVALID, "w2a_step_host: NULL argument");
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = h->n;
+  uint2* sstat = plane_static(h->state);
+  uint2* smut = plane_mut(h->state, n);
+  // one kernel variant for the whole batch, so that chunking never changes a result bit
+  const int variant = n < 32768 ? W2A_STEP_THREAD : W2A_STEP_COOP;
+  int ci = 0;
+  for (int64_t c0 = 0; c0 < n; c0 += kHostChunk, ++ci) {
+    const int64_t m = std::min(kHostChunk, n - c0);
+    const size_t um = static_cast<size_t>(m);
+    cudaStream_t st = h->streams[ci % kHostStreams];
+    W2A_CUDA(ctx, cudaMemcpyAsync(h->action + c0, action + c0, um, cudaMemcpyHostToDevice, st));
+    int rc = step_planes(ctx, st, m, h->action + c0, W2A_ACT_U8, sstat + c0, smut + c0,
+                         h->obs + c0 * W2A_OBS_DIM, h->reward + c0, h->terminated + c0,
+                         remaining ? h->remaining + c0 : nullptr, at_budget ? h->at_budget + c0 : nullptr,
+                         variant);
+    if (rc) return rc;
+    W2A_CUDA(ctx, cudaMemcpyAsync(obs + c0 * W2A_OBS_DIM, h->obs + c0 * W2A_OBS_DIM,
+                                  um * W2A_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+    W2A_CUDA(ctx, cudaMemcpyAsync(reward + c0, h->reward + c0, um * 4, cudaMemcpyDeviceToHost, st));
+    W2A_CUDA(ctx, cudaMemcpyAsync(terminated + c0, h->terminated + c0, um, cudaMemcpyDeviceToHost, st));
+    if (remaining)
+      W2A_CUDA(ctx, cudaMemcpyAsync(remaining + c0, h->remaining + c0, um * 4, cudaMemcpyDeviceToHost, st));
+    if (at_budget)
+      W2A_CUDA(ctx, cudaMemcpyAsync(at_budget + c0, h->at_budget + c0, um, cudaMemcpyDeviceToHost, st));
+  }
+  for (auto& s : h->streams) W2A_CUDA(ctx, cudaStreamSynchronize(s));
+  return W2A_OK;
+}
+
+int64_t w2a_launch_count(const w2a_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -18,11 +18,17 @@
 //     streams (state, action, obs, reward, flags) use streaming (.cs) accesses so they
 //     do not evict the tables.
 #pragma once
+#ifndef W2A_KO
+#define W2A_KO 0
+#endif
+
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
 
 namespace w2a {
+__device__ __forceinline__ double cvt_w(float w) { return (W2A_KO & 128) ? __hiloint2double(__float_as_int(w), 0) : static_cast<double>(w); }
+__device__ __forceinline__ float cvt_o(double x) { return (W2A_KO & 128) ? __int_as_float(__double2hiint(x)) : static_cast<float>(x); }
 
 constexpr int kObsDim = 29;
 constexpr int kXStride = 32;   // float64 per day-row record
@@ -216,10 +222,10 @@ __device__ __forceinline__ LaneSlots lane_slots(int q) {
 #define W2A_COOP_WARPS 8  // warps per CTA
 #endif
 #ifndef W2A_COOP_MINBLOCKS
-#define W2A_COOP_MINBLOCKS 2  // CTAs per SM the register allocation is sized for (B200 sweep: profiles/r01)
+#define W2A_COOP_MINBLOCKS 3  // CTAs per SM the register allocation is sized for
 #endif
 #ifndef W2A_COOP_AHEAD
-#define W2A_COOP_AHEAD 4  // rounds of table loads in flight ahead of the one being consumed
+#define W2A_COOP_AHEAD 2  // rounds of table loads in flight ahead of the one being consumed
 #endif
 constexpr int kCoopWarps = W2A_COOP_WARPS;
 constexpr int kAhead = W2A_COOP_AHEAD;
@@ -241,8 +247,8 @@ struct RoundLoads {
 __device__ __forceinline__ RoundLoads issue_round(const double2* x_lane, const float4* w_lane, unsigned row,
                                                   unsigned cv) {
   RoundLoads r;
-  const double2* xr = x_lane + static_cast<size_t>(row) * (kXStride / 2);
-  const float4* wr = w_lane + static_cast<size_t>(cv) * (kWStride / 4);
+  const double2* xr = x_lane + static_cast<size_t>((W2A_KO & 16) ? (row & 63u) : row) * (kXStride / 2);
+  const float4* wr = w_lane + static_cast<size_t>((W2A_KO & 32) ? (cv & 63u) : cv) * (kWStride / 4);
   r.xa = __ldg(xr);
   r.xb = __ldg(xr + 8);
   r.wa = __ldg(wr);
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
       a_n = load_action<ADT>(p.action, ecn);
     }
     const Transition tr = advance(sv, mv, a);
-    if (valid) st_stream(p.st_mut + e, mv);
+    if (valid && !(W2A_KO & 8)) st_stream(p.st_mut + e, mv);
     const unsigned cv = sv.y;
     const bool write_obs = valid && !tr.done;  // on and after the last day the previous obs stands (Q2)
     const unsigned wmask = __ballot_sync(kFull, write_obs);
@@ -342,6 +348,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
     // ---- phase B ---------------------------------------------------------------------------
     // kAhead rounds of loads are in flight while a round is being consumed
     RoundLoads ring[kAhead + 1];
+    double acc_b = 0.0, acc_e = 0.0;
 #pragma unroll
     for (int d = 0; d < kAhead; ++d) {
       const unsigned rowd = __shfl_sync(kFull, tr.row, d, 8);
@@ -356,18 +363,20 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
         ring[(it + kAhead) % (kAhead + 1)] = issue_round(x_lane, w_lane, rowd, cvd);
       }
       const RoundLoads& cur = ring[it % (kAhead + 1)];
-      const double pb = fma(cur.xa.x, static_cast<double>(cur.wa.x), cur.xa.y * static_cast<double>(cur.wa.z)) +
-                        fma(cur.xb.x, static_cast<double>(cur.wb.x), cur.xb.y * static_cast<double>(cur.wb.z));
-      const double pe = fma(cur.xa.x, static_cast<double>(cur.wa.y), cur.xa.y * static_cast<double>(cur.wa.w)) +
-                        fma(cur.xb.x, static_cast<double>(cur.wb.y), cur.xb.y * static_cast<double>(cur.wb.w));
-      part_w[it * 32 + ((lane ^ it) - lane)] = make_double2(pb, pe);
+      const double pb = fma(cur.xa.x, cvt_w(cur.wa.x), cur.xa.y * cvt_w(cur.wa.z)) +
+                        fma(cur.xb.x, cvt_w(cur.wb.x), cur.xb.y * cvt_w(cur.wb.z));
+      const double pe = fma(cur.xa.x, cvt_w(cur.wa.y), cur.xa.y * cvt_w(cur.wa.w)) +
+                        fma(cur.xb.x, cvt_w(cur.wb.y), cur.xb.y * cvt_w(cur.wb.w));
+      if (!(W2A_KO & 256)) part_w[it * 32 + ((lane ^ it) - lane)] = make_double2(pb, pe); else { acc_b += pb; acc_e += pe; }
       if (q >= 6) oth_w[it * 8] = cur.wb;
       // observation of day t (Q2): float32 of the table slots this lane holds
       float* const sa = st_a + it * kObsDim;
-      sa[0] = static_cast<float>(cur.xa.x);
-      sa[1] = static_cast<float>(cur.xa.y);
-      if (ls.bx >= 0) st_bx[it * kObsDim] = static_cast<float>(cur.xb.x);
-      if (ls.by >= 0) st_by[it * kObsDim] = static_cast<float>(cur.xb.y);
+      if (!(W2A_KO & 64)) {
+      sa[0] = cvt_o(cur.xa.x);
+      sa[1] = cvt_o(cur.xa.y);
+      if (ls.bx >= 0) st_bx[it * kObsDim] = cvt_o(cur.xb.x);
+      if (ls.by >= 0) st_by[it * kObsDim] = cvt_o(cur.xb.y);
+      }
     }
     __syncwarp();
 
@@ -388,9 +397,9 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
       ze = fma(f_rem, static_cast<double>(o1.y), ze);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const double2 v = ws.part[q][(lane & 24) | (j ^ q)];
+        if (!(W2A_KO & 256)) { const double2 v = ws.part[q][(lane & 24) | (j ^ q)];
         zb += v.x;
-        ze += v.y;
+        ze += v.y; } else { zb += acc_b; ze += acc_e; }
       }
       // the four agent slots and the significance NaN of this env's staged observation row
       my_row[23] = static_cast<float>(tr.lag);
@@ -400,12 +409,15 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
       my_row[28] = static_cast<float>(tr.cnt14);
       if (valid) {
         // reward = -1000/152 * sigmoid(z_b) * (1 - sigmoid(z_e) * [heat_qi > 0.5] * action)  (env.py:211-221)
-        const double baseline = expit(zb);
-        const double eff = tr.act ? expit(ze) : 0.0;
-        __stcs(p.reward + e, static_cast<float>(kRewardScale * baseline * (1.0 - eff)));
+        const double baseline = (W2A_KO & 4) ? zb : expit(zb);
+        const double eff = (W2A_KO & 4) ? ze : (tr.act ? expit(ze) : 0.0);
+        const float rw = static_cast<float>(kRewardScale * baseline * (1.0 - eff));
+        if (!(W2A_KO & 2)) {
+        __stcs(p.reward + e, rw);
         p.terminated[e] = static_cast<uint8_t>(tr.done);
         if (p.remaining) __stcs(p.remaining + e, tr.rem);
         if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
+        } else if (rw == 123.f) p.reward[e] = rw;
       }
     }
     fence_proxy_async_smem();  // staged observation rows -> visible to the bulk-copy engine
@@ -413,8 +425,8 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
     // observation rows: 32 x 116 B contiguous in global memory (base is a multiple of 32)
     float* const ob = p.obs + static_cast<size_t>(base) * kObsDim;
     if (wmask == kFull && obs_aligned) {
-      if (lane == 0) bulk_store(ob, ws.obs, kObsBlockBytes);
-      bulk_pending = true;
+      if (!(W2A_KO & 1)) { if (lane == 0) bulk_store(ob, ws.obs, kObsBlockBytes);
+      bulk_pending = true; }
     } else if (wmask != 0u) {  // ragged tail or some envs already on their last day
       for (int i = lane; i < 32 * kObsDim; i += 32) {
         const int env = (i * 565) >> 14;  // i / 29 for i < 928

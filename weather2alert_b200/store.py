@@ -20,6 +20,8 @@ from . import schema
 X_STRIDE = 32  # float64 per day-row record
 W_STRIDE = 64  # float32 per coefficient record
 X_SIG = 24  # record position of the significance code
+X_GATE = 25  # record position of the heat_qi gate column: 0.0 if heat_qi > 0.5 else GATE_OFF
+GATE_OFF = -1e300  # times the constant effectiveness coefficient 1.0: sigmoid(z_e) becomes exactly 0
 W_OTHER = 56  # first float of the non-table coefficients (lag1, streak, remaining, bias)
 
 
@@ -78,11 +80,14 @@ class FeatureStore:
     def pack_x(self) -> np.ndarray:
         """float64 [S*Y*T, 32] day-row records: positions 0..23 the reward features that are
         read from the table (obs slots 0..22 and 26), 24 the significance code with 0.0 for
-        "none" (the kernels show it as NaN), 25..31 zero."""
+        "none" (the kernels show it as NaN), 25 the heat_qi gate column, 26..31 zero."""
         S, Y, T = self.shape
         out = np.zeros((S * Y * T, X_STRIDE), dtype=np.float64)
         out[:, :24] = self.feat[..., list(schema.TABLE_REWARD_SLOTS)].reshape(S * Y * T, 24)
         out[:, X_SIG] = np.nan_to_num(self.sig_code.reshape(-1).astype(np.float64), nan=0.0)
+        # env.py:218 `effectiveness * (heat_qi > 0.5)` (quirk Q4) as a table column (NaN compares False)
+        heat_qi = self.feat[..., schema.SLOT_HEAT_QI].reshape(-1)
+        out[:, X_GATE] = np.where(heat_qi > 0.5, 0.0, GATE_OFF)
         return out
 
     # ---- constructors -----------------------------------------------------------------
@@ -164,12 +169,14 @@ class RewardWeights:
 
     def pack(self) -> np.ndarray:
         """float32 [S*P, 64] coefficient records: record ``col*P + p`` = 24 table features x
-        (b,e), 8 zeros, then the four non-table terms x (b,e) (see `coef_pos_*`)."""
+        (b,e), the gate column's (0,1) at floats 50,51 inside 8 otherwise-zero floats, then the four
+        non-table terms x (b,e) (see `coef_pos_*`)."""
         P, S = self.coef.shape[:2]
         out = np.zeros((S, P, W_STRIDE), dtype=np.float32)
         c = np.transpose(self.coef, (1, 0, 2, 3))  # [S, P, 2, 28]
         out[:, :, _COEF_POS] = c[:, :, 0, :]
         out[:, :, _COEF_POS + 1] = c[:, :, 1, :]
+        out[:, :, 2 * X_GATE + 1] = 1.0  # effectiveness coefficient of the gate column
         return out.reshape(S * P, W_STRIDE)
 
     @classmethod
