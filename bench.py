@@ -226,11 +226,16 @@ def run_ours(args):
     ms_max = float(ms_t.item())
     value = n * world * K / (ms_max * 1e-3)
 
-    # optional return-statistics reduction (the only collective of the path)
-    stats = torch.stack([reward.double().sum(), (reward.double() ** 2).sum(),
-                         torch.tensor(float(n), dtype=torch.float64, device=dev), rem.double().sum()])
-    if world > 1:
-        dist.all_reduce(stats)
+    # return statistics of one full summer (untimed), then the only collective of the path:
+    # one all-reduce of the sufficient statistics (NCCL over NVLink when world > 1)
+    from weather2alert_b200.distributed import RolloutStats, summarize
+
+    rs = RolloutStats(n, dev)
+    do_reset()
+    for tt in range(T):
+        step(actions[tt])
+        rs.update(actions[tt], reward, term, atb)
+    stats = summarize(rs.reduce())
 
     # ---- end to end through the host-buffer C entry points: `e2e` ---------------------------------
     e2e = None
@@ -290,8 +295,7 @@ def run_ours(args):
                      "note": "achieved = streaming bytes (HBM-mandatory) x envs / mean step time over the timed region"},
         "roofline_canonical_466B": {"achieved": ach_c, "frac": ach_c / peak,
                                     "note": "SURVEY 8(d) canonical 466 B/env-step; includes table gathers served from L2"},
-        "return_stats": {"sum_reward": float(stats[0]), "sum_reward_sq": float(stats[1]), "n": float(stats[2]),
-                         "sum_remaining": float(stats[3]), "reduced_over": world},
+        "return_stats": {**stats, "reduced_over": world},
     }
     traffic_file = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(traffic_file):

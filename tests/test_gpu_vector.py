@@ -122,3 +122,32 @@ def test_million_envs_properties(big_core):
     ob, rb, _, _ = run(2, half, n)
     assert torch.equal(torch.cat([oa, ob]).view(torch.int32), o2.view(torch.int32))  # shards == whole
     assert torch.equal(torch.cat([ra, rb]), r2)
+
+
+def test_vector_env_rollout_stats(golden):
+    """track_stats=True accumulates the callback statistics on the device (callbacks.py:63-74)."""
+    from weather2alert_b200 import HeatAlertVectorEnv
+    from weather2alert_b200.distributed import summarize
+
+    n = 128
+    env = HeatAlertVectorEnv(n, weights=golden.weights("std"), store=golden.store(), seed=3, years=[2006],
+                             track_stats=True)
+    env.reset()
+    rng = np.random.default_rng(0)
+    ret = np.zeros(n)
+    finished, alerts, refused = [], 0, 0
+    for _ in range(153 * 2):
+        a = rng.random(n) < 0.3
+        atb_before = env._rem.cpu().numpy() == 0
+        obs, rew, term, _, info = env.step(torch.from_numpy(a).cuda())
+        ret += rew.cpu().numpy().astype(np.float64)
+        alerts += int((a & ~atb_before).sum())
+        refused += int((a & atb_before).sum())
+        d = term.cpu().numpy()
+        finished += list(ret[d])
+        ret[d] = 0
+    s = summarize(env.stats.reduce())
+    assert s["episodes"] == len(finished) == 2 * n and s["steps"] == 153 * 2 * n
+    assert s["alerts"] == alerts and s["refused_at_budget"] == refused
+    assert s["mean_return"] == pytest.approx(np.mean(finished), rel=1e-9)
+    assert s["std_return"] == pytest.approx(np.std(finished), rel=1e-6)

@@ -1,0 +1,69 @@
+"""Env sharding and the one collective of the path: the reduction of return statistics.
+
+Envs are independent (all state of the reference env lives in the env object,
+`/root/reference/src/weather2alert/env.py:156-180`), so N GPUs step N contiguous shards
+with replicated tables and no step-time communication.  What is worth reducing are the
+rollout statistics the reference's SB3 callback logs
+(`/root/reference/src/weather2alert/callbacks.py:63-74`: mean return, over-budget
+frequency, alert frequency, ...); their sufficient statistics are a short float64 vector
+that is all-reduced once per rollout (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+STAT_NAMES = ("episodes", "return_sum", "return_sq_sum", "steps", "alerts", "refused_at_budget")
+N_STATS = len(STAT_NAMES)
+
+
+def shard_bounds(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous shard [lo, hi) of `n_total` envs for `rank`; sizes differ by at most one."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} not in [0, {world})")
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class RolloutStats:
+    """Device-side accumulator of the return statistics of one rank's envs."""
+
+    def __init__(self, num_envs: int, device):
+        self.ep_return = torch.zeros(num_envs, dtype=torch.float64, device=device)
+        self.totals = torch.zeros(N_STATS, dtype=torch.float64, device=device)
+
+    def update(self, actions, reward, terminated, at_budget):
+        """One step: `actions` any integer/bool dtype, `at_budget` the pre-action flag."""
+        a = actions.bool() if actions.dtype != torch.bool else actions
+        atb = at_budget.bool()
+        self.ep_return += reward.double()
+        done = terminated.bool()
+        fin = torch.where(done, self.ep_return, torch.zeros_like(self.ep_return))
+        upd = torch.stack([done.sum().double(), fin.sum(), (fin * fin).sum(),
+                           torch.tensor(float(reward.numel()), dtype=torch.float64, device=reward.device),
+                           (a & ~atb).sum().double(), (a & atb).sum().double()])
+        self.totals += upd
+        self.ep_return.masked_fill_(done, 0.0)
+
+    def reduce(self, group=None) -> torch.Tensor:
+        return reduce_stats(self.totals.clone(), group)
+
+
+def reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum a `[N_STATS]` float64 vector over all ranks (no-op without a process group)."""
+    if stats.shape[-1] != N_STATS or stats.dtype != torch.float64:
+        raise ValueError(f"expected float64[..., {N_STATS}]")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def summarize(stats: torch.Tensor) -> dict:
+    """The quantities `AlertLoggingCallback` reports (callbacks.py:63-74) from the reduced vector."""
+    s = dict(zip(STAT_NAMES, (float(v) for v in stats.tolist())))
+    n_ep, n_steps = max(s["episodes"], 1.0), max(s["steps"], 1.0)
+    mean = s["return_sum"] / n_ep
+    var = max(s["return_sq_sum"] / n_ep - mean * mean, 0.0)
+    return {**s, "mean_return": mean, "std_return": var ** 0.5,
+            "alert_freq": s["alerts"] / n_steps, "over_budget_freq": s["refused_at_budget"] / n_steps}

@@ -49,6 +49,7 @@ class HeatAlertVectorEnv:
         autoreset: bool = True,
         core: HeatAlertCore | None = None,
         step_variant: int = _lib.STEP_AUTO,
+        track_stats: bool = False,
     ):
         if core is None:
             if store is None or not isinstance(weights, RewardWeights):
@@ -99,6 +100,12 @@ class HeatAlertVectorEnv:
         self._rem = torch.zeros(n, dtype=torch.int32, device=dev)
         self._atb = torch.zeros(n, dtype=torch.bool, device=dev)
         self._bound = {}
+        # rollout statistics a la AlertLoggingCallback (callbacks.py:63-74); `stats.reduce()` all-reduces them
+        self.stats = None
+        if track_stats:
+            from .distributed import RolloutStats
+
+            self.stats = RolloutStats(n, dev)
         self._idx = {}        # index streams of the most recent draw (device int32)
         self._list_idx = torch.zeros(n, dtype=torch.int32, device=dev)  # county (fips_list index) per env
         self._term_at = None  # device int64[n]: step number at which each env terminates
@@ -225,6 +232,8 @@ class HeatAlertVectorEnv:
                 self._state, self._obs, self._reward, self._term.view(torch.uint8), self._rem,
                 self._atb.view(torch.uint8), variant=self.step_variant, action_dtype=actions.dtype)
         fn(actions)
+        if self.stats is not None:
+            self.stats.update(actions, self._reward, self._term, self._atb)
         self._step_no += 1
         if self.autoreset and self._step_no >= self._next_term:
             if self._term_at is None:
