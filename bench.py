@@ -75,9 +75,10 @@ def make_tables(years=N_YEARS, counties=S_COUNTIES, samples=P_SAMPLES):
     return store, weights
 
 
-def index_streams(store, weights, n, rank, augment):
+def index_streams(store, weights, n, rank, augment, locality="interleaved"):
     """env i -> county (global i) mod S; year / posterior sample / similar-list index drawn with
-    numpy's default_rng(1234 + rank)."""
+    numpy's default_rng(1234 + rank).  locality="sorted" assigns
+    the SAME multiset of episodes to env slots in (county, sample, year) order."""
     from weather2alert_b200.sampling import EpisodeSampler
 
     rng = np.random.default_rng(1234 + rank)
@@ -85,6 +86,9 @@ def index_streams(store, weights, n, rank, augment):
     list_idx = (np.arange(n, dtype=np.int64) + rank * n) % S
     sp = EpisodeSampler(store, weights)
     s = sp.draw_bulk(rng, n, list_idx, augment)
+    if locality == "sorted":
+        order = np.lexsort((s["year"], s["coef_idx"], s["coef_col"], s["loc"]))
+        s = {k: np.ascontiguousarray(v[order]) for k, v in s.items()}
     return s
 
 
@@ -165,7 +169,7 @@ def run_ours(args):
     t_setup = time.time()
     store, weights = make_tables()
     core = HeatAlertCore(store, weights, dev)
-    s = index_streams(store, weights, n, rank, wl["augment"])
+    s = index_streams(store, weights, n, rank, wl["augment"], args.locality)
     idx = {k: torch.from_numpy(v).to(dev) for k, v in s.items()}
     T = int(store.n_days.max())
     variant = {"auto": _lib.STEP_AUTO, "thread": _lib.STEP_THREAD, "coop": _lib.STEP_COOP}[args.variant]
@@ -281,7 +285,7 @@ def run_ours(args):
         "config": {"workload": args.workload, "desc": wl["desc"], "envs_per_gpu": n, "envs_total": n * world,
                    "counties": S_COUNTIES, "years": N_YEARS, "days": T, "posterior_samples": P_SAMPLES,
                    "weights": "linear-format synthetic (nn_* checkpoints share the layout and the path)",
-                   "augment": wl["augment"], "mode": "per-step launches", "variant": args.variant,
+                   "augment": wl["augment"], "mode": "per-step launches", "locality": args.locality, "variant": args.variant,
                    "parallelism": f"env-sharded x{world}, no step-time collective",
                    "l2": "per-step streaming traffic (151 B x envs) exceeds the 126 MB L2 for >= 2^20 envs; "
                          "tables (feature rows of the day + coefficients) are meant to stay L2-resident"},
@@ -308,7 +312,7 @@ def run_ours(args):
             pass
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_port(store, weights, args.cpu_seconds)
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -392,7 +396,7 @@ def run_reference(args):
                "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"]},
                "cpu_baseline": cb,
                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out), flush=True)
+        emit(out)
         return
 
     from weather2alert_b200 import synthetic
@@ -444,10 +448,28 @@ def run_reference(args):
            "config": {"workload": args.workload, "desc": wl["desc"], "envs_total": n_workers * envs_per_worker},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_workers, "kind": "reference", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Library banners (e.g. NCCL's version line) go to stderr; fd 1 carries only the JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3060)
@@ -456,6 +478,7 @@ def main():
     ap.add_argument("--workload", choices=list(WORKLOADS), default="cfg3_1m")
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--variant", choices=["auto", "thread", "coop"], default="auto")
+    ap.add_argument("--locality", choices=["interleaved", "sorted"], default="interleaved")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
