@@ -241,6 +241,33 @@ def run_ours(args):
         rs.update(actions[tt], reward, term, atb)
     stats = summarize(rs.reduce())
 
+    # the same summer through the episode-fused rollout kernel (one launch for all T steps, no
+    # observations): an extra, not the headline metric
+    ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
+    ro_stats = torch.zeros(6, dtype=torch.float64, device=dev)
+    ro_ms = []
+    for _ in range(3):
+        do_reset()
+        ep_ret.zero_()
+        ro_stats.zero_()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        r0.record()
+        core.rollout(state, T, ep_ret, actions=actions, stats=ro_stats)
+        r1.record()
+        torch.cuda.synchronize()
+        ro_ms.append(r0.elapsed_time(r1))
+    ro_t = torch.tensor([min(ro_ms[1:])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ro_t, op=dist.ReduceOp.MAX)
+    from weather2alert_b200.distributed import reduce_stats
+
+    ro_sum = summarize(reduce_stats(ro_stats))
+    rollout_info = {"value": n * world * T / (float(ro_t.item()) * 1e-3), "unit": UNIT, "ms_per_rollout": float(ro_t.item()),
+                    "steps_per_rollout": T, "kernel": "rollout_kernel (episode-fused, obs elided)",
+                    "mean_return": ro_sum["mean_return"],
+                    "same_returns_as_stepping": bool(abs(ro_sum["mean_return"] - stats["mean_return"]) <= 1e-6 * abs(stats["mean_return"]))}
+
     # ---- end to end through the host-buffer C entry points: `e2e` ---------------------------------
     e2e = None
     if not args.no_e2e:
@@ -300,6 +327,7 @@ def run_ours(args):
         "roofline_canonical_466B": {"achieved": ach_c, "frac": ach_c / peak,
                                     "note": "SURVEY 8(d) canonical 466 B/env-step; includes table gathers served from L2"},
         "return_stats": {**stats, "reduced_over": world},
+        "rollout": rollout_info,
     }
     traffic_file = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(traffic_file):

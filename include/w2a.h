@@ -124,6 +124,21 @@ int w2a_step(w2a_ctx* ctx, void* stream, int64_t n, const void* action, int acti
              void* state, float* obs, float* reward, uint8_t* terminated,
              int32_t* remaining, uint8_t* at_budget, int variant);
 
+/* The whole `while not done: env.step(a)` loop (env.py:273-276) of `n` envs in one launch:
+ * up to `steps` steps per env, stopping at the env's terminal step; envs that are already
+ * done are left alone.  Observations are not materialised.
+ *   actions    dev uint8 [steps, n] row-major (row k = the k-th step of this call), or NULL:
+ *              then action(env, k) = hash(seed, env, k) < p_alert * 2^32 (Bernoulli(p_alert),
+ *              counter based -- see rollout_hash in w2a_kernels.cuh)
+ *   state      in/out
+ *   ep_return  dev float64 [n], += the float64 sum of this call's rewards of the env
+ *   stats      dev float64 [6] or NULL, += {episodes finished, sum and sum of squares of their
+ *              ep_return, steps, alerts issued, alerts refused at budget}: the sufficient
+ *              statistics of the reference's AlertLoggingCallback (callbacks.py:63-74), ready
+ *              for one all-reduce across GPUs */
+int w2a_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, const uint8_t* actions,
+                uint64_t seed, float p_alert, void* state, double* ep_return, double* stats);
+
 /* ---- host-buffer entry points: the call a CPU-side RL loop makes ------------------
  * The context owns a device-resident env set; every call copies its inputs from and its
  * outputs to HOST memory (pinned for full PCIe speed), pipelined in chunks over several

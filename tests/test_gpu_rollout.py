@@ -1,0 +1,113 @@
+"""The episode-fused rollout kernel against step-by-step execution and against the oracle."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed, n, short=True):
+    from weather2alert_b200 import synthetic
+
+    rng = np.random.default_rng(seed)
+    S, Y, P = 30, 3, 16
+    fips, zones = synthetic.synthetic_counties(S, seed=seed)
+    n_days = np.full((S, Y), 153, np.uint8)
+    if short:
+        n_days[rng.integers(0, S, 6), rng.integers(0, Y, 6)] = rng.integers(1, 152, 6)
+    store = synthetic.make_store(fips, [2006, 2007, 2008], seed=seed + 1, zones=zones, n_days=n_days, p_alert=0.08)
+    weights = synthetic.make_weights(fips, P, seed=seed + 2)
+    idx = dict(loc=rng.integers(0, S, n), year=rng.integers(0, Y, n), coef_col=rng.integers(0, S, n),
+               coef_idx=rng.integers(0, P, n), budget=rng.integers(-1, 12, n))
+    return store, weights, {k: v.astype(np.int32) for k, v in idx.items()}
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("n", [1, 3, 130, 4099])
+def test_rollout_equals_stepping_and_oracle(n):
+    """Action bank: chunks of 61 + 61 + 61 steps (crossing chunk-of-8 boundaries and episode ends)
+    must leave the same state as 183 `step` launches, and the same returns as the oracle."""
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200.core import HeatAlertCore
+    from weather2alert_b200.distributed import STAT_NAMES
+
+    store, weights, idx = _case(100 + n, n)
+    core = HeatAlertCore(store, weights, "cuda:0")
+    d = {k: _dev(v) for k, v in idx.items()}
+    rng = np.random.default_rng(9)
+    total = 183
+    acts = (rng.random((total, n)) < 0.35).astype(np.uint8)
+
+    def fresh():
+        st = core.alloc_state(n)
+        obs = torch.zeros((n, 29), device="cuda")
+        core.reset(st, obs, d["loc"], d["year"], d["coef_col"], d["coef_idx"], budget=d["budget"])
+        return st, obs
+
+    # (1) fused rollout in three calls
+    st_r, _ = fresh()
+    ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    stats = torch.zeros(6, dtype=torch.float64, device="cuda")
+    for c in range(3):
+        core.rollout(st_r, 61, ret, actions=_dev(acts[61 * c:61 * (c + 1)]), stats=stats)
+    # (2) oracle, stopping every env at its terminal step
+    ost, _ = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"], idx["coef_col"],
+                             idx["coef_idx"], idx["budget"])
+    ret_ref = np.zeros(n)
+    alive = np.ones(n, bool)
+    n_steps = alerts = refused = 0
+    # (3) the step kernel, frozen per env at its terminal step
+    st_s, obs = fresh()
+    reward = torch.zeros(n, device="cuda")
+    term = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    frozen = st_s.clone().view(2, n, 8)
+    for k in range(total):
+        before = ost["budget"] - ost["hist"].sum(axis=1)
+        _, r, dn, rem, atb = orc.batch_step(store.feat, store.sig_code, weights.coef, ost, acts[k])
+        ret_ref += np.where(alive, r, 0.0)
+        n_steps += int(alive.sum())
+        alerts += int(((before - rem) * alive).sum())
+        refused += int(((acts[k] != 0) & atb & alive).sum())
+        core.step(st_s, _dev(acts[k]), obs, reward, term, variant=2)
+        cur = st_s.view(2, n, 8)
+        al = torch.from_numpy(alive).cuda()
+        frozen[:, al] = cur[:, al]
+        alive &= ~dn
+    np.testing.assert_allclose(ret.cpu().numpy(), ret_ref, rtol=1e-9, atol=1e-12)
+    assert torch.equal(st_r.view(2, n, 8), frozen)
+    s = dict(zip(STAT_NAMES, stats.cpu().tolist()))
+    finished = ~alive
+    assert s["episodes"] == finished.sum() and s["steps"] == n_steps
+    assert s["alerts"] == alerts and s["refused_at_budget"] == refused
+    assert s["return_sum"] == pytest.approx(ret_ref[finished].sum(), rel=1e-9)
+    assert s["return_sq_sum"] == pytest.approx((ret_ref[finished] ** 2).sum(), rel=1e-9)
+    # a finished env is left alone by further rollouts
+    snap = st_r.clone()
+    core.rollout(st_r, 10, ret, actions=_dev(acts[:10]), stats=stats)
+    assert torch.equal(st_r.view(2, n, 8)[:, torch.from_numpy(finished).cuda()],
+                       snap.view(2, n, 8)[:, torch.from_numpy(finished).cuda()])
+
+
+def test_rollout_hash_actions_match_host_stream(golden):
+    """actions=None: the in-kernel Bernoulli stream equals `rollout_action_bits` on the host."""
+    from weather2alert_b200 import HeatAlertVectorEnv
+    from weather2alert_b200.distributed import rollout_action_bits
+
+    n = 257
+    env_a = HeatAlertVectorEnv(n, weights=golden.weights("std"), store=golden.store(), seed=5, years=[2006], autoreset=False)
+    env_b = HeatAlertVectorEnv(n, weights=golden.weights("std"), store=golden.store(), seed=5, years=[2006], autoreset=False)
+    env_a.reset()
+    env_b.reset()
+    ret_a, stats_a = env_a.rollout(p_alert=0.3, seed=77)
+    bits = rollout_action_bits(77, np.arange(n), np.arange(153), 0.3)
+    assert 0.25 < bits.mean() < 0.35
+    ret_b, stats_b = env_b.rollout(actions=torch.from_numpy(bits))
+    assert torch.equal(ret_a, ret_b)
+    # counts are exact; the float sums go through atomics whose order is not fixed
+    assert torch.equal(stats_a[[0, 3, 4, 5]], stats_b[[0, 3, 4, 5]])
+    assert torch.allclose(stats_a, stats_b, rtol=1e-12, atol=0)
+    assert torch.equal(env_a._state, env_b._state)
+    assert float(stats_a[0]) == n and float(stats_a[3]) == 153 * n

@@ -30,6 +30,7 @@ SIGNATURES = {
     "w2a_state_bytes": (C.c_size_t, [C.c_int64]),
     "w2a_reset": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "w2a_step": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int]),
+    "w2a_rollout": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_uint64, C.c_float, _P, _P, _P]),
     "w2a_host_envs_create": (C.c_int, [_P, C.c_int64]),
     "w2a_host_envs_destroy": (C.c_int, [_P]),
     "w2a_reset_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -130,6 +130,17 @@ class HeatAlertCore:
 
         return step
 
+    def rollout(self, state, steps: int, ep_return, actions=None, seed: int = 0, p_alert: float = 0.5, stats=None):
+        """Episode-fused rollout (`w2a_rollout`): up to `steps` steps per env in one launch."""
+        n = ep_return.numel()
+        self._check_dev("state", state, torch.uint8, n * 16)
+        self._check_dev("ep_return", ep_return, torch.float64, n)
+        self._check_dev("stats", stats, torch.float64, 6)
+        if actions is not None:
+            self._check_dev("actions", actions, (torch.uint8, torch.bool), int(steps) * n)
+        _lib.check(self._lib.w2a_rollout(self.ctx, self._stream(), n, int(steps), _ptr(actions), int(seed) & (2**64 - 1),
+                                         float(p_alert), _ptr(state), _ptr(ep_return), _ptr(stats)), self.ctx)
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.w2a_launch_count(self.ctx))

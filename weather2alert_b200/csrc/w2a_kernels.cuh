@@ -483,4 +483,212 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
   }
 }
 
+// =========================================================================================
+// rollout: the whole `while not done: step(a)` loop (env.py:273-276) of every env in one
+// launch.  Observations are not materialised; what comes out is the sum of rewards per env,
+// the advanced state, and the sufficient statistics of the reference's logging callback
+// (callbacks.py:63-74).
+//
+// 8 lanes per env, 4 envs per warp, and time is processed in chunks of 8 days:
+//   * the env's coefficient record is loaded and converted to float64 ONCE (registers);
+//   * per day, lane q loads record positions {2q,2q+1} and {16+2q,17+2q} of the day-row
+//     (the env's days are consecutive 256-byte records) and accumulates its partial logits;
+//   * a transposing shuffle butterfly hands day (chunk, q) to lane q: the 8 lanes of an env
+//     evaluate 8 different days' sigmoids at once;
+//   * the integer recurrence of the chunk (budget clamp, streak, 14-day window) depends on
+//     actions only, never on rewards, so every lane replays it from the chunk's 8 action
+//     bits and picks the values of its own day.
+// Actions come from a [steps, n] byte bank or from a counter-based Bernoulli(p) hash.
+// An env that is already done is left alone (unlike `step`, quirk Q11).
+// =========================================================================================
+struct RolloutArgs {
+  Tables tb;
+  const uint2* st_static;
+  uint2* st_mut;
+  const uint8_t* actions;  // [steps, n] or null
+  unsigned long long seed;
+  unsigned threshold;      // P(action = 1) * 2^32 when actions == null
+  double* ep_return;       // [n], +=
+  double* stats;           // [6], += (episodes, return_sum, return_sq_sum, steps, alerts, refused_at_budget)
+  int n, steps;
+};
+
+// One butterfly level of the transposing reduction: lanes whose bit is set keep the upper
+// half of the values and send the lower half, and vice versa; after levels 4, 2, 1 lane q of
+// an 8-lane group holds the group's sum of value q.
+template <int N>
+__device__ __forceinline__ void fold_level(double (&v)[N], bool upper, int lane_xor) {
+#pragma unroll
+  for (int k = 0; k < N / 2; ++k) {
+    const double keep = upper ? v[k + N / 2] : v[k];
+    const double send = upper ? v[k] : v[k + N / 2];
+    v[k] = keep + __shfl_xor_sync(kFull, send, lane_xor);
+  }
+}
+
+// counter-based action stream: bit = hash(seed, env, step) < threshold   (splitmix64 finaliser)
+__host__ __device__ __forceinline__ unsigned rollout_hash(unsigned long long seed, unsigned env, unsigned step) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((static_cast<unsigned long long>(env) << 20) ^ step ^ 0x5851F42D4C957F2Dull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<unsigned>(z >> 32);
+}
+
+__global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
+  __shared__ double s_stats[6];
+  if (threadIdx.x < 6) s_stats[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 7;
+  const int g = lane >> 3;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int n_quads = (p.n + 3) >> 2;  // 4 envs per warp iteration
+  const double2* const x_lane = reinterpret_cast<const double2*>(p.tb.x) + q;
+  double st_eps = 0.0, st_ret = 0.0, st_sq = 0.0, st_steps = 0.0, st_alerts = 0.0, st_ref = 0.0;
+
+  for (int wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wq < n_quads; wq += warps_total) {
+    const int e = wq * 4 + g;
+    const bool valid = e < p.n;
+    const int ec = valid ? e : p.n - 1;
+    const uint2 sv = __ldg(p.st_static + ec);
+    const uint2 mv = __ldg(p.st_mut + ec);
+    const int n_days = sv.x >> 24;
+    const unsigned row0 = sv.x & 0xffffffu;
+    int rem = static_cast<int>(mv.x);
+    int t = mv.y & 0xff;
+    int streak = (mv.y >> 8) & 0xff;
+    unsigned win = (mv.y >> 16) & 0x3fffu;
+    bool done = ((mv.y >> 30) & 1u) != 0 || !valid;
+
+    // coefficient record -> float64 registers, once per episode
+    const float4* wr = reinterpret_cast<const float4*>(p.tb.w + static_cast<size_t>(sv.y) * kWStride);
+    const float4 wa4 = __ldg(wr + q), wb4 = __ldg(wr + 8 + q);
+    const float4 o0 = __ldg(wr + 14), o1 = __ldg(wr + 15);  // (b,e) of lag1, streak | remaining, bias
+    const double wab0 = wa4.x, wae0 = wa4.y, wab1 = wa4.z, wae1 = wa4.w;
+    const double wbb0 = wb4.x, wbe0 = wb4.y, wbb1 = wb4.z, wbe1 = wb4.w;
+    const double c_lag_b = o0.x, c_lag_e = o0.y, c_str_b = o0.z, c_str_e = o0.w;
+    const double c_rem_b = o1.x, c_rem_e = o1.y, c_bias_b = o1.z, c_bias_e = o1.w;
+
+    double ret = 0.0;
+    int k = 0;  // steps taken by this env in this call
+    // the 4 envs of a warp may need different numbers of chunks: loop while any is alive
+    while (__any_sync(kFull, !done && k < p.steps)) {
+      const bool live = !done && k < p.steps;
+      // days this env executes in this chunk: t .. t+nv-1, the last one possibly terminal
+      const int nv = live ? min(8, min(p.steps - k, n_days - t)) : 0;
+      // ---- table part of the logits of the chunk's days ----------------------------------
+      double pbv[8], pev[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const unsigned row = row0 + static_cast<unsigned>(min(t + j, n_days - 1));
+        const double2* xr = x_lane + static_cast<size_t>(row) * (kXStride / 2);
+        const double2 xa = __ldg(xr), xb = __ldg(xr + 8);
+        pbv[j] = fma(xa.x, wab0, xa.y * wab1) + fma(xb.x, wbb0, xb.y * wbb1);
+        pev[j] = fma(xa.x, wae0, xa.y * wae1) + fma(xb.x, wbe0, xb.y * wbe1);
+      }
+      // ---- this chunk's 8 action bits: lane q fetches day q's ------------------------------
+      int a_mine = 0;
+      if (q < nv) {
+        if (p.actions) a_mine = __ldg(p.actions + static_cast<size_t>(k + q) * p.n + e) != 0;
+        else a_mine = rollout_hash(p.seed, static_cast<unsigned>(e), static_cast<unsigned>(k + q)) < p.threshold;
+      }
+      const unsigned am = (__ballot_sync(kFull, a_mine) >> (8 * g)) & 0xffu;
+      // ---- integer recurrence of the chunk (env.py:242-250), replayed by every lane -----------
+      unsigned actm = 0, refm = 0;
+      {
+        int r = rem;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned a = (am >> j) & 1u;
+          const unsigned atb = (r == 0) ? 1u : 0u;
+          const unsigned act = a & ~atb;
+          r -= static_cast<int>(act);
+          actm |= act << j;
+          refm |= (a & atb) << j;
+        }
+      }
+      // ---- transpose: lane q gets the table logits of day q ---------------------------------
+      fold_level<8>(pbv, (q & 4) != 0, 4);
+      fold_level<8>(pev, (q & 4) != 0, 4);
+      double b4[4] = {pbv[0], pbv[1], pbv[2], pbv[3]}, e4[4] = {pev[0], pev[1], pev[2], pev[3]};
+      fold_level<4>(b4, (q & 2) != 0, 2);
+      fold_level<4>(e4, (q & 2) != 0, 2);
+      double b2[2] = {b4[0], b4[1]}, e2[2] = {e4[0], e4[1]};
+      fold_level<2>(b2, (q & 1) != 0, 1);
+      fold_level<2>(e2, (q & 1) != 0, 1);
+      // ---- lane q evaluates day q (env.py:190-193, 206-221; quirk Q1) --------------------------
+      double r_mine = 0.0;
+      if (q < nv) {
+        const unsigned below = actm & ((1u << q) - 1u);
+        const int act = (actm >> q) & 1;
+        const int rem_after = rem - __popc(actm & ((2u << q) - 1u));
+        const unsigned zeros = ~below & ((1u << q) - 1u);
+        const int streak_q = zeros == 0u ? streak + q : q - 1 - (31 - __clz(zeros));
+        const int lag = (t + q) > 0 ? act : 0;
+        double zb = b2[0] + c_bias_b, ze = e2[0] + c_bias_e;
+        zb = fma(static_cast<double>(lag), c_lag_b, zb);
+        ze = fma(static_cast<double>(lag), c_lag_e, ze);
+        zb = fma(static_cast<double>(streak_q), c_str_b, zb);
+        ze = fma(static_cast<double>(streak_q), c_str_e, ze);
+        zb = fma(static_cast<double>(rem_after), c_rem_b, zb);
+        ze = fma(static_cast<double>(rem_after), c_rem_e, ze);
+        const double baseline = expit(zb);
+        const double eff = act ? expit(ze) : 0.0;
+        r_mine = kRewardScale * baseline * (1.0 - eff);
+      }
+      r_mine += __shfl_xor_sync(kFull, r_mine, 4);
+      r_mine += __shfl_xor_sync(kFull, r_mine, 2);
+      r_mine += __shfl_xor_sync(kFull, r_mine, 1);
+      ret += r_mine;
+      // ---- carry the state over the chunk (env.py:256-260) -------------------------------------
+      if (nv > 0) {
+        const unsigned vmask = (1u << nv) - 1u;  // nv <= 8
+        const bool terminal = (t + nv) >= n_days;  // the chunk's last day is the episode's last
+        // the streak is not updated on the terminal day
+        const int ns = terminal ? nv - 1 : nv;
+        const unsigned sm = (1u << ns) - 1u;
+        const unsigned zeros = ~actm & sm;
+        streak = zeros == 0u ? streak + ns : ns - 1 - (31 - __clz(zeros));
+        rem -= __popc(actm & vmask);
+        // the window keeps the most recent action in bit 0, the chunk mask has day j in bit j
+        win = ((win << nv) | (__brev(actm & vmask) >> (32 - nv))) & 0x3fffu;
+        t = terminal ? n_days - 1 : t + nv;
+        k += nv;
+        if (q == 0) {
+          st_steps += nv;
+          st_alerts += __popc(actm & vmask);
+          st_ref += __popc(refm & vmask);
+        }
+        if (terminal) done = true;
+      }
+    }
+    if (valid && q == 0 && k > 0) {
+      const double total = p.ep_return[e] + ret;
+      p.ep_return[e] = total;
+      p.st_mut[e] = make_uint2(static_cast<unsigned>(rem),
+                               static_cast<unsigned>(t) | (static_cast<unsigned>(streak) << 8) | (win << 16) |
+                                   ((done ? 1u : 0u) << 30));
+      if (done) {
+        st_eps += 1.0;
+        st_ret += total;
+        st_sq += total * total;
+      }
+    }
+  }
+  // ---- statistics: lanes -> block (shared atomics) -> one global atomic per block and field ---
+  if (p.stats) {
+    if (q == 0) {
+      atomicAdd(&s_stats[0], st_eps);
+      atomicAdd(&s_stats[1], st_ret);
+      atomicAdd(&s_stats[2], st_sq);
+      atomicAdd(&s_stats[3], st_steps);
+      atomicAdd(&s_stats[4], st_alerts);
+      atomicAdd(&s_stats[5], st_ref);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 && s_stats[threadIdx.x] != 0.0) atomicAdd(p.stats + threadIdx.x, s_stats[threadIdx.x]);
+  }
+}
+
 }  // namespace w2a

@@ -67,3 +67,21 @@ def summarize(stats: torch.Tensor) -> dict:
     var = max(s["return_sq_sum"] / n_ep - mean * mean, 0.0)
     return {**s, "mean_return": mean, "std_return": var ** 0.5,
             "alert_freq": s["alerts"] / n_steps, "over_budget_freq": s["refused_at_budget"] / n_steps}
+
+
+def rollout_action_bits(seed: int, envs, steps, p_alert: float):
+    """The counter-based action stream of `w2a_rollout(actions=NULL)` on the host:
+    ``bits[k, i] = hash(seed, envs[i], steps[k]) < p_alert * 2**32`` (splitmix64 finaliser; same
+    arithmetic as `rollout_hash` in csrc/w2a_kernels.cuh).  Returns bool [len(steps), len(envs)]."""
+    import numpy as np
+
+    e = np.asarray(envs, dtype=np.uint64)[None, :]
+    k = np.asarray(steps, dtype=np.uint64)[:, None]
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & (2**64 - 1)) + np.uint64(0x9E3779B97F4A7C15) * ((e << np.uint64(20)) ^ k ^ np.uint64(0x5851F42D4C957F2D))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    thr = p_alert * 4294967296.0
+    thr = 0xFFFFFFFF if thr >= 4294967295.0 else int(thr)
+    return (z >> np.uint64(32)) < np.uint64(thr)

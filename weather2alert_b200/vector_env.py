@@ -242,6 +242,33 @@ class HeatAlertVectorEnv:
                 self._reset_subset((self._term_at <= self._step_no).to(torch.uint8))
         return self._obs, self._reward, self._term, self._trunc, self._infos()
 
+    # ---- episode-fused rollout ------------------------------------------------------------------
+    def rollout(self, steps: int | None = None, actions: torch.Tensor | None = None, p_alert: float = 0.5,
+                seed: int = 0, stats: torch.Tensor | None = None):
+        """Run up to `steps` steps (default: to the end of the summer) of every env in ONE kernel
+        launch -- the `while not done: step(a)` loop of `env.py:273-276` without materialising
+        observations.  `actions` is a ``uint8/bool [steps, N]`` CUDA tensor, or None for
+        counter-based Bernoulli(`p_alert`) actions (`rollout_action_bits` reproduces them).
+        Returns ``(episode_return float64[N], stats float64[6])``; `stats` (see
+        `distributed.STAT_NAMES`) is accumulated into, so it can be carried across calls and
+        all-reduced with `distributed.reduce_stats`.  Envs that finish are NOT auto-reset."""
+        if self._next_term is None:
+            raise RuntimeError("call reset() before rollout()")
+        if steps is None:
+            steps = int(self.store.n_days.max())
+        if actions is not None:
+            if actions.dtype == torch.bool:
+                actions = actions.view(torch.uint8)
+            actions = actions.to(self.device).contiguous()
+            if actions.shape != (steps, self.num_envs):
+                raise ValueError(f"actions must have shape ({steps}, {self.num_envs})")
+        if stats is None:
+            stats = torch.zeros(6, dtype=torch.float64, device=self.device)
+        ep_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        self.core.rollout(self._state, steps, ep_return, actions=actions, seed=seed, p_alert=p_alert, stats=stats)
+        self._step_no += steps
+        return ep_return, stats
+
     def _infos(self):
         return {"remaining_budget": self._rem, "at_budget": self._atb, "location_index": self._list_idx}
 
