@@ -129,6 +129,11 @@ class HeatAlertVectorEnv:
                 s["budget"] = torch.as_tensor(np.ascontiguousarray(src["budget"], dtype=np.int32)).to(dev)
             s["list_idx"] = (torch.as_tensor(np.ascontiguousarray(src["list_idx"], dtype=np.int32)).to(dev)
                              if "list_idx" in src else s["coef_col"])
+            for key, hi in (("loc", self.core.S), ("year", self.core.Y), ("coef_col", self.core.Sw),
+                            ("coef_idx", self.core.P)):
+                a = np.asarray(src[key])
+                if a.shape != (n,) or (a < 0).any() or (a >= hi).any():
+                    raise IndexError(f"index_streams[{key!r}] must hold {n} values in [0, {hi})")
             nd = self.store.n_days[np.asarray(src["loc"]), np.asarray(src["year"])]
             if (nd == 0).any():
                 bad = int(np.argmax(nd == 0))
