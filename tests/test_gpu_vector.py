@@ -151,3 +151,17 @@ def test_vector_env_rollout_stats(golden):
     assert s["alerts"] == alerts and s["refused_at_budget"] == refused
     assert s["mean_return"] == pytest.approx(np.mean(finished), rel=1e-9)
     assert s["std_return"] == pytest.approx(np.std(finished), rel=1e-6)
+
+
+def test_sort_episodes_is_a_permutation_of_the_same_draws(golden):
+    from weather2alert_b200 import HeatAlertVectorEnv
+
+    kw = dict(weights=golden.weights("std"), store=golden.store(), seed=9, similar_climate_counties=True)
+    a = HeatAlertVectorEnv(500, **kw)
+    b = HeatAlertVectorEnv(500, sort_episodes=True, **kw)
+    a.reset()
+    b.reset()
+    ka = torch.stack([a._idx[k] for k in ("loc", "coef_col", "coef_idx", "year")], 1).cpu().numpy()
+    kb = torch.stack([b._idx[k] for k in ("loc", "coef_col", "coef_idx", "year")], 1).cpu().numpy()
+    assert sorted(map(tuple, ka)) == list(map(tuple, kb))  # same multiset, lexicographic order
+    assert torch.equal(b._list_idx, b._idx["list_idx"])

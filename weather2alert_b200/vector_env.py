@@ -50,6 +50,7 @@ class HeatAlertVectorEnv:
         core: HeatAlertCore | None = None,
         step_variant: int = _lib.STEP_AUTO,
         track_stats: bool = False,
+        sort_episodes: bool = False,
     ):
         if core is None:
             if store is None or not isinstance(weights, RewardWeights):
@@ -66,6 +67,10 @@ class HeatAlertVectorEnv:
         self.budget = budget
         self.autoreset = autoreset
         self.step_variant = step_variant
+        # Assign the sampled episodes to env slots in (county, coefficient column, sample, year)
+        # order.  The draws are i.i.d., so which slot gets which episode is immaterial, but
+        # neighbouring envs then share table lines (profiles/r01: +8 % per step, +35 % per rollout).
+        self.sort_episodes = sort_episodes
         self.sampler = EpisodeSampler(self.store, self.weights, years)
         self.fips_list = self.sampler.fips_list
         self.single_observation_space = spaces.Box(-np.inf, np.inf, (schema.OBS_DIM,), np.float32)
@@ -165,6 +170,10 @@ class HeatAlertVectorEnv:
             if bool(bad.any()):  # the reference raises KeyError at env.py:127 / datautils.py:123
                 b = int(torch.nonzero(bad)[0])
                 raise KeyError((sp.fips_list[int(list_idx[b])], int(year[b])))
+        if self.sort_episodes:
+            key = ((loc * self.core.Sw + coef_col) * sp.n_samples + coef_idx) * self.core.Y + year
+            order = torch.argsort(key)
+            loc, year, coef_col, coef_idx, list_idx = (v[order] for v in (loc, year, coef_col, coef_idx, list_idx))
         s = dict(loc=loc.int(), year=year.int(), coef_col=coef_col.int(), coef_idx=coef_idx.int(),
                  list_idx=list_idx.int())
         budget = o.get("budget", self.budget)
