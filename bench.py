@@ -330,6 +330,27 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # BASELINE configs[0] on the GPU: the single-env drop-in class, one summer, random policy
+    single = None
+    if not args.no_e2e:
+        from weather2alert_b200 import HeatAlertEnv
+
+        env1 = HeatAlertEnv(weights=weights, store=store, device=str(dev))
+        loc1 = "06037" if "06037" in weights.fips_list else weights.fips_list[0]
+        env1.reset(location=loc1, seed=1234)
+        arng = np.random.default_rng(7)
+        for _ in range(5):
+            env1.step(int(arng.integers(2)))
+        env1.reset(location=loc1, seed=1234)
+        s0 = time.perf_counter()
+        nst, done1 = 0, False
+        while not done1:
+            _, _, done1, _, _ = env1.step(int(arng.integers(2)))
+            nst += 1
+        single = {"ms_per_step": (time.perf_counter() - s0) / nst * 1e3, "steps": nst,
+                  "api": "HeatAlertEnv.reset(location, seed=1234) / .step(a): batch of one through w2a_step_host"}
+        env1.close()
+
     peak, peak_src = load_peaks()
     sec_per_step = ms_max * 1e-3 / K
     ach = BYTES_STREAMING * n / sec_per_step / 1e9
@@ -359,6 +380,7 @@ def run_ours(args):
                                     "note": "SURVEY 8(d) canonical 466 B/env-step; includes table gathers served from L2"},
         "return_stats": {**stats, "reduced_over": world},
         "rollout": rollout_info,
+        "single_env": single,
     }
     traffic_file = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
