@@ -228,7 +228,7 @@ constexpr int kAhead = W2A_COOP_AHEAD;
 struct __align__(128) WarpScratch {
   float obs[32 * kObsDim];  // the warp's 32 observation rows, same layout as in global memory (3712 B)
   float4 other[8][8];       // [round][2*group + (lane-6)]: raw non-table coefficients for the env's owner
-  double2 part[8][32];      // [round][lane ^ round]: (pb, pe) partial dot products
+  double2 part[8][32];      // [round][8*group + (lane%8 ^ swizzle)]: (pb, pe) partial dot products
 };
 constexpr int kCoopSmemBytes = kCoopWarps * static_cast<int>(sizeof(WarpScratch));
 constexpr unsigned kObsBlockBytes = 32 * kObsDim * sizeof(float);
@@ -268,7 +268,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // step, variant COOP: a warp owns 32 consecutive envs.
 //
 //   phase A  one thread per env: coalesced state/action traffic and the integer transition.
-//   phase B  eight rounds, four envs per round, 8 lanes per env: four 128-bit loads per
+//   phase B  eight rounds, four consecutive envs per round, 8 lanes per env: four 128-bit loads per
 //            lane fetch the env's day-row and coefficient record (the next round's loads
 //            are issued before this round's math); the lane's float64 partial dot products
 //            and the float32 copies of its observation slots go to shared memory.  The
@@ -292,13 +292,21 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
   const double2* const x_lane = reinterpret_cast<const double2*>(p.tb.x) + q;
   const float4* const w_lane = reinterpret_cast<const float4*>(p.tb.w) + q;
   const LaneSlots ls = lane_slots(q);
-  // staging pointers of this lane inside its group's rows; round `it` adds it*29 floats
-  float* const st_a = ws.obs + (lane & 24) * kObsDim + 2 * q;
-  float* const st_bx = ws.obs + (lane & 24) * kObsDim + (ls.bx >= 0 ? ls.bx : 0);
-  float* const st_by = ws.obs + (lane & 24) * kObsDim + (ls.by >= 0 ? ls.by : 0);
-  double2* const part_w = &ws.part[0][lane];                        // + it*32 + ((lane^it) - lane)
+  // Round `it` serves envs 4*it .. 4*it+3 of the warp, group g taking env 4*it+g: neighbouring
+  // envs that share a day-row or a coefficient record (locality-sorted env sets) then fall
+  // into the same load instruction and share its cache-line wavefronts.
+  // staging pointers of this lane inside its env's row; round `it` adds 4*it rows
+  float* const st_a = ws.obs + g * kObsDim + 2 * q;
+  float* const st_bx = ws.obs + g * kObsDim + (ls.bx >= 0 ? ls.bx : 0);
+  float* const st_by = ws.obs + g * kObsDim + (ls.by >= 0 ? ls.by : 0);
+  // partials: slot [it][8g + (q ^ s)], s = 4*(it&1) + g, so that the 8 owner threads of a
+  // quarter-warp (two rounds x four groups) read 8 different bank quads
+  double2* const part_even = &ws.part[0][8 * g + (q ^ g)];          // even rounds: + it*32
+  double2* const part_odd = &ws.part[0][8 * g + (q ^ (4 + g))];     // odd rounds:  + it*32
   float4* const oth_w = &ws.other[0][2 * g + (q & 1)];              // lanes 6,7: + it*8
   float* const my_row = ws.obs + lane * kObsDim;
+  const int my_it = lane >> 2, my_g = lane & 3;                     // the round and group that served env `lane`
+  const int my_swz = 4 * (my_it & 1) + my_g;
   const bool obs_aligned = (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
   bool bulk_pending = false;
 
@@ -344,15 +352,15 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
     RoundLoads ring[kAhead + 1];
 #pragma unroll
     for (int d = 0; d < kAhead; ++d) {
-      const unsigned rowd = __shfl_sync(kFull, tr.row, d, 8);
-      const unsigned cvd = __shfl_sync(kFull, cv, d, 8);
+      const unsigned rowd = __shfl_sync(kFull, tr.row, 4 * d + g);
+      const unsigned cvd = __shfl_sync(kFull, cv, 4 * d + g);
       ring[d] = issue_round(x_lane, w_lane, rowd, cvd);
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       if (it + kAhead < 8) {
-        const unsigned rowd = __shfl_sync(kFull, tr.row, it + kAhead, 8);
-        const unsigned cvd = __shfl_sync(kFull, cv, it + kAhead, 8);
+        const unsigned rowd = __shfl_sync(kFull, tr.row, 4 * (it + kAhead) + g);
+        const unsigned cvd = __shfl_sync(kFull, cv, 4 * (it + kAhead) + g);
         ring[(it + kAhead) % (kAhead + 1)] = issue_round(x_lane, w_lane, rowd, cvd);
       }
       const RoundLoads& cur = ring[it % (kAhead + 1)];
@@ -360,23 +368,23 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
                         fma(cur.xb.x, static_cast<double>(cur.wb.x), cur.xb.y * static_cast<double>(cur.wb.z));
       const double pe = fma(cur.xa.x, static_cast<double>(cur.wa.y), cur.xa.y * static_cast<double>(cur.wa.w)) +
                         fma(cur.xb.x, static_cast<double>(cur.wb.y), cur.xb.y * static_cast<double>(cur.wb.w));
-      part_w[it * 32 + ((lane ^ it) - lane)] = make_double2(pb, pe);
+      ((it & 1) ? part_odd : part_even)[it * 32] = make_double2(pb, pe);
       if (q >= 6) oth_w[it * 8] = cur.wb;
       // observation of day t (Q2): float32 of the table slots this lane holds
-      float* const sa = st_a + it * kObsDim;
+      float* const sa = st_a + it * (4 * kObsDim);
       sa[0] = static_cast<float>(cur.xa.x);
       sa[1] = static_cast<float>(cur.xa.y);
-      if (ls.bx >= 0) st_bx[it * kObsDim] = static_cast<float>(cur.xb.x);
-      if (ls.by >= 0) st_by[it * kObsDim] = static_cast<float>(cur.xb.y);
+      if (ls.bx >= 0) st_bx[it * (4 * kObsDim)] = static_cast<float>(cur.xb.x);
+      if (ls.by >= 0) st_by[it * (4 * kObsDim)] = static_cast<float>(cur.xb.y);
     }
     __syncwarp();
 
     // ---- phase C ---------------------------------------------------------------------------
-    // env (lane) was round q of its 8-lane group: partials in part[q][(g*8+j)^q], its non-table
-    // coefficients in other[q][2g], other[q][2g+1]
+    // env (lane) was served in round lane/4 by group lane%4: partials in part[my_it][8*my_g + (j ^ my_swz)],
+    // its non-table coefficients in other[my_it][2*my_g], other[my_it][2*my_g + 1]
     {
-      const float4 o0 = ws.other[q][2 * g];      // (b,e) of alert_lag1, alert_streak
-      const float4 o1 = ws.other[q][2 * g + 1];  // (b,e) of remaining_budget, bias
+      const float4 o0 = ws.other[my_it][2 * my_g];      // (b,e) of alert_lag1, alert_streak
+      const float4 o1 = ws.other[my_it][2 * my_g + 1];  // (b,e) of remaining_budget, bias
       double zb = static_cast<double>(o1.z), ze = static_cast<double>(o1.w);
       const double f_lag = static_cast<double>(tr.lag), f_streak = static_cast<double>(tr.streak),
                    f_rem = static_cast<double>(tr.rem);
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
       ze = fma(f_rem, static_cast<double>(o1.y), ze);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const double2 v = ws.part[q][(lane & 24) | (j ^ q)];
+        const double2 v = ws.part[my_it][8 * my_g + (j ^ my_swz)];
         zb += v.x;
         ze += v.y;
       }
@@ -459,14 +467,15 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const unsigned rowj = __shfl_sync(kFull, row0, it, 8);
-      const int takej = __shfl_sync(kFull, static_cast<int>(take), it, 8);
+      const int j = 4 * it + (lane >> 3);  // env of the warp served by this lane's group in this round
+      const unsigned rowj = __shfl_sync(kFull, row0, j);
+      const int takej = __shfl_sync(kFull, static_cast<int>(take), j);
       if (takej) {
         const double2* xr = x_lane + static_cast<size_t>(rowj) * (kXStride / 2);
         const double2 xa = __ldg(xr), xb = __ldg(xr + 8);
         float vbx = static_cast<float>(xb.x);
         if (q == 4) vbx = sig_to_obs(vbx);
-        float* ob = p.obs + static_cast<size_t>(base + (lane & 24) + it) * kObsDim;
+        float* ob = p.obs + static_cast<size_t>(base + j) * kObsDim;
         st_stream(ob + 2 * q, static_cast<float>(xa.x));
         st_stream(ob + 2 * q + 1, static_cast<float>(xa.y));
         if (ls.bx >= 0) st_stream(ob + ls.bx, vbx);
