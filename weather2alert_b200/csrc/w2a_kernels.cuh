@@ -310,34 +310,52 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
   const bool obs_aligned = (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
   bool bulk_pending = false;
 
-  // per-env inputs of the first group; those of the next group are fetched one group ahead
+  // Software pipeline over the warp's groups of 32 envs: while group G is in phase C (fold,
+  // sigmoids, stores), the state transition of group G+1 is already done and its first
+  // kAhead rounds of table loads are in flight; the per-env inputs of group G+2 are being
+  // fetched.  `cur_*` belong to G, `nxt_*` to G+1, `in_*` are raw inputs one step further.
   int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  uint2 sv_n = make_uint2(0u, 0u), mv_n = make_uint2(0u, 0u);
-  int a_n = 0;
-  if (wg < n_groups) {
-    const int ec0 = min((wg << 5) + lane, p.n - 1);
-    sv_n = ld_stream(p.st_static + ec0);
-    mv_n = ld_stream(p.st_mut + ec0);
-    a_n = load_action<ADT>(p.action, ec0);
-  }
+  RoundLoads ring[kAhead + 1];
+  uint2 in_sv = make_uint2(0u, 0u), in_mv = make_uint2(0u, 0u);
+  int in_a = 0;
+  auto fetch_inputs = [&](int group) {
+    if (group < n_groups) {
+      const int ec = min((group << 5) + lane, p.n - 1);
+      in_sv = ld_stream(p.st_static + ec);
+      in_mv = ld_stream(p.st_mut + ec);
+      in_a = load_action<ADT>(p.action, ec);
+    }
+  };
+  Transition cur_tr = {};
+  unsigned cur_cv = 0u;
+  // phase A of `group` from the fetched inputs + its first kAhead rounds of loads
+  auto open_group = [&](int group) {
+    if (group < n_groups) {
+      const uint2 sv = in_sv;
+      uint2 mv = in_mv;
+      const int a = in_a;
+      cur_tr = advance(sv, mv, a);
+      const int e = (group << 5) + lane;
+      if (e < p.n) st_stream(p.st_mut + e, mv);
+      cur_cv = sv.y;
+#pragma unroll
+      for (int d = 0; d < kAhead; ++d) {
+        const unsigned rowd = __shfl_sync(kFull, cur_tr.row, 4 * d + g);
+        const unsigned cvd = __shfl_sync(kFull, cur_cv, 4 * d + g);
+        ring[d] = issue_round(x_lane, w_lane, rowd, cvd);
+      }
+    }
+  };
+  fetch_inputs(wg);
+  open_group(wg);
+  fetch_inputs(wg + warps_total);
+
   for (; wg < n_groups; wg += warps_total) {
     const int base = wg << 5;
     const int e = base + lane;
     const bool valid = e < p.n;
-
-    // ---- phase A ---------------------------------------------------------------------------
-    const uint2 sv = sv_n;
-    uint2 mv = mv_n;
-    const int a = a_n;
-    if (wg + warps_total < n_groups) {
-      const int ecn = min(((wg + warps_total) << 5) + lane, p.n - 1);
-      sv_n = ld_stream(p.st_static + ecn);
-      mv_n = ld_stream(p.st_mut + ecn);
-      a_n = load_action<ADT>(p.action, ecn);
-    }
-    const Transition tr = advance(sv, mv, a);
-    if (valid) st_stream(p.st_mut + e, mv);
-    const unsigned cv = sv.y;
+    const Transition tr = cur_tr;
+    const unsigned cv = cur_cv;
     const bool write_obs = valid && !tr.done;  // on and after the last day the previous obs stands (Q2)
     const unsigned wmask = __ballot_sync(kFull, write_obs);
     // the previous group's bulk store must have finished reading the staging buffer
@@ -349,13 +367,6 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
 
     // ---- phase B ---------------------------------------------------------------------------
     // kAhead rounds of loads are in flight while a round is being consumed
-    RoundLoads ring[kAhead + 1];
-#pragma unroll
-    for (int d = 0; d < kAhead; ++d) {
-      const unsigned rowd = __shfl_sync(kFull, tr.row, 4 * d + g);
-      const unsigned cvd = __shfl_sync(kFull, cv, 4 * d + g);
-      ring[d] = issue_round(x_lane, w_lane, rowd, cvd);
-    }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       if (it + kAhead < 8) {
@@ -378,6 +389,10 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
       if (ls.by >= 0) st_by[it * (4 * kObsDim)] = static_cast<float>(cur.xb.y);
     }
     __syncwarp();
+
+    // ---- open the next group: its loads fly while this one finishes --------------------------------
+    open_group(wg + warps_total);
+    fetch_inputs(wg + 2 * warps_total);
 
     // ---- phase C ---------------------------------------------------------------------------
     // env (lane) was served in round lane/4 by group lane%4: partials in part[my_it][8*my_g + (j ^ my_swz)],
