@@ -268,7 +268,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // step, variant COOP: a warp owns 32 consecutive envs.
 //
 //   phase A  one thread per env: coalesced state/action traffic and the integer transition.
-//   phase B  eight rounds, four consecutive envs per round, 8 lanes per env: four 128-bit loads per
+//   phase B  eight rounds, four envs per round, 8 lanes per env: four 128-bit loads per
 //            lane fetch the env's day-row and coefficient record (the next round's loads
 //            are issued before this round's math); the lane's float64 partial dot products
 //            and the float32 copies of its observation slots go to shared memory.  The
@@ -292,21 +292,26 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
   const double2* const x_lane = reinterpret_cast<const double2*>(p.tb.x) + q;
   const float4* const w_lane = reinterpret_cast<const float4*>(p.tb.w) + q;
   const LaneSlots ls = lane_slots(q);
-  // Round `it` serves envs 4*it .. 4*it+3 of the warp, group g taking env 4*it+g: neighbouring
-  // envs that share a day-row or a coefficient record (locality-sorted env sets) then fall
-  // into the same load instruction and share its cache-line wavefronts.
-  // staging pointers of this lane inside its env's row; round `it` adds 4*it rows
-  float* const st_a = ws.obs + g * kObsDim + 2 * q;
-  float* const st_bx = ws.obs + g * kObsDim + (ls.bx >= 0 ? ls.bx : 0);
-  float* const st_by = ws.obs + g * kObsDim + (ls.by >= 0 ? ls.by : 0);
-  // partials: slot [it][8g + (q ^ s)], s = 4*(it&1) + g, so that the 8 owner threads of a
-  // quarter-warp (two rounds x four groups) read 8 different bank quads
-  double2* const part_even = &ws.part[0][8 * g + (q ^ g)];          // even rounds: + it*32
-  double2* const part_odd = &ws.part[0][8 * g + (q ^ (4 + g))];     // odd rounds:  + it*32
-  float4* const oth_w = &ws.other[0][2 * g + (q & 1)];              // lanes 6,7: + it*8
+  // Round m serves envs {2m, 2m+1, 2m+16, 2m+17} of the warp, group g taking env
+  // row_of(m, g) = 2m + (g & 1) + 16 (g >> 1).  Two reasons for this composition:
+  //   * neighbouring envs (2m, 2m+1) that share a day-row or a coefficient record in a
+  //     locality-sorted env set fall into the same load instruction and share its lines;
+  //   * with 29-float rows the four staged rows start at banks b, b+29, b+16, b+13 (mod 32):
+  //     the 8 even-or-odd banks a group writes per store never collide with another group's.
+  const int row_g = (g & 1) + 16 * (g >> 1);  // env of round 0 for this group; round m adds 2m
+  float* const st_a = ws.obs + row_g * kObsDim + 2 * q;
+  float* const st_bx = ws.obs + row_g * kObsDim + (ls.bx >= 0 ? ls.bx : 0);
+  float* const st_by = ws.obs + row_g * kObsDim + (ls.by >= 0 ? ls.by : 0);
+  // partials: slot [m][8g + (q ^ s)], s = 2*(m & 3) + (g & 1), so that the 8 owner threads of a
+  // quarter-warp (four rounds x two groups) read 8 different bank quads
+  double2* part_w[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) part_w[r] = &ws.part[0][8 * g + (q ^ (2 * r + (g & 1)))];  // round m: part_w[m & 3] + 32 m
+  float4* const oth_w = &ws.other[0][2 * g + (q & 1)];              // lanes 6,7: + 8 m
   float* const my_row = ws.obs + lane * kObsDim;
-  const int my_it = lane >> 2, my_g = lane & 3;                     // the round and group that served env `lane`
-  const int my_swz = 4 * (my_it & 1) + my_g;
+  // the round and group that served env `lane`
+  const int my_it = (lane & 15) >> 1, my_g = (lane & 1) + 2 * (lane >> 4);
+  const int my_swz = 2 * (my_it & 3) + (my_g & 1);
   const bool obs_aligned = (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
   bool bulk_pending = false;
 
@@ -340,8 +345,8 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
       cur_cv = sv.y;
 #pragma unroll
       for (int d = 0; d < kAhead; ++d) {
-        const unsigned rowd = __shfl_sync(kFull, cur_tr.row, 4 * d + g);
-        const unsigned cvd = __shfl_sync(kFull, cur_cv, 4 * d + g);
+        const unsigned rowd = __shfl_sync(kFull, cur_tr.row, 2 * d + row_g);
+        const unsigned cvd = __shfl_sync(kFull, cur_cv, 2 * d + row_g);
         ring[d] = issue_round(x_lane, w_lane, rowd, cvd);
       }
     }
@@ -370,8 +375,8 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       if (it + kAhead < 8) {
-        const unsigned rowd = __shfl_sync(kFull, tr.row, 4 * (it + kAhead) + g);
-        const unsigned cvd = __shfl_sync(kFull, cv, 4 * (it + kAhead) + g);
+        const unsigned rowd = __shfl_sync(kFull, tr.row, 2 * (it + kAhead) + row_g);
+        const unsigned cvd = __shfl_sync(kFull, cv, 2 * (it + kAhead) + row_g);
         ring[(it + kAhead) % (kAhead + 1)] = issue_round(x_lane, w_lane, rowd, cvd);
       }
       const RoundLoads& cur = ring[it % (kAhead + 1)];
@@ -379,14 +384,14 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
                         fma(cur.xb.x, static_cast<double>(cur.wb.x), cur.xb.y * static_cast<double>(cur.wb.z));
       const double pe = fma(cur.xa.x, static_cast<double>(cur.wa.y), cur.xa.y * static_cast<double>(cur.wa.w)) +
                         fma(cur.xb.x, static_cast<double>(cur.wb.y), cur.xb.y * static_cast<double>(cur.wb.w));
-      ((it & 1) ? part_odd : part_even)[it * 32] = make_double2(pb, pe);
+      part_w[it & 3][it * 32] = make_double2(pb, pe);
       if (q >= 6) oth_w[it * 8] = cur.wb;
       // observation of day t (Q2): float32 of the table slots this lane holds
-      float* const sa = st_a + it * (4 * kObsDim);
+      float* const sa = st_a + it * (2 * kObsDim);
       sa[0] = static_cast<float>(cur.xa.x);
       sa[1] = static_cast<float>(cur.xa.y);
-      if (ls.bx >= 0) st_bx[it * (4 * kObsDim)] = static_cast<float>(cur.xb.x);
-      if (ls.by >= 0) st_by[it * (4 * kObsDim)] = static_cast<float>(cur.xb.y);
+      if (ls.bx >= 0) st_bx[it * (2 * kObsDim)] = static_cast<float>(cur.xb.x);
+      if (ls.by >= 0) st_by[it * (2 * kObsDim)] = static_cast<float>(cur.xb.y);
     }
     __syncwarp();
 
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
     fetch_inputs(wg + 2 * warps_total);
 
     // ---- phase C ---------------------------------------------------------------------------
-    // env (lane) was served in round lane/4 by group lane%4: partials in part[my_it][8*my_g + (j ^ my_swz)],
+    // env (lane) was served in round my_it by group my_g: partials in part[my_it][8*my_g + (j ^ my_swz)],
     // its non-table coefficients in other[my_it][2*my_g], other[my_it][2*my_g + 1]
     {
       const float4 o0 = ws.other[my_it][2 * my_g];      // (b,e) of alert_lag1, alert_streak
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const int j = 4 * it + (lane >> 3);  // env of the warp served by this lane's group in this round
+      const int j = 2 * it + ((lane >> 3) & 1) + 16 * (lane >> 4);  // env served by this lane's group in this round
       const unsigned rowj = __shfl_sync(kFull, row0, j);
       const int takej = __shfl_sync(kFull, static_cast<int>(take), j);
       if (takej) {
