@@ -273,7 +273,7 @@ def run_ours(args):
     # the same summer through the episode-fused rollout kernel (one launch for all T steps, no
     # observations): an extra, not the headline metric
     ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
-    ro_stats = torch.zeros(6, dtype=torch.float64, device=dev)
+    ro_stats = torch.zeros(15, dtype=torch.float64, device=dev)
     ro_ms = []
     for _ in range(3):
         do_reset()

@@ -57,6 +57,7 @@ extern "C" {
 /* per-env budget value meaning "use the episode's historical budget"
  * (env.py:167-170: `self.ep["remaining_budget"].iloc[0]`). */
 #define W2A_BUDGET_DEFAULT INT32_MIN
+#define W2A_NUM_STATS 15
 
 typedef struct w2a_ctx w2a_ctx;
 
@@ -132,10 +133,14 @@ int w2a_step(w2a_ctx* ctx, void* stream, int64_t n, const void* action, int acti
  *              counter based -- see rollout_hash in w2a_kernels.cuh)
  *   state      in/out
  *   ep_return  dev float64 [n], += the float64 sum of this call's rewards of the env
- *   stats      dev float64 [6] or NULL, += {episodes finished, sum and sum of squares of their
- *              ep_return, steps, alerts issued, alerts refused at budget}: the sufficient
- *              statistics of the reference's AlertLoggingCallback (callbacks.py:63-74), ready
- *              for one all-reduce across GPUs */
+ *   stats      dev float64 [W2A_NUM_STATS] or NULL, += the sufficient statistics of the reference's
+ *              AlertLoggingCallback (callbacks.py:63-74), ready for one all-reduce across GPUs:
+ *              0 episodes finished, 1-2 sum / sum of squares of their ep_return, 3 steps,
+ *              4 alerts issued, 5 alerts refused at budget, 6-7 sum / sum of squares of the day
+ *              of summer of every issued alert, 8-10 count / sum / sum of squares of the lengths
+ *              of streaks of issued alerts that ended, 11-13 sums of the day by which 50 %, 80 %,
+ *              100 % of a summer's alerts had been issued, 14 summers counted in 11-13 (those
+ *              with at least one alert that ran from day 0 within this call) */
 int w2a_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, const uint8_t* actions,
                 uint64_t seed, float p_alert, void* state, double* ep_return, double* stats);
 

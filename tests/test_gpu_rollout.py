@@ -50,7 +50,7 @@ def test_rollout_equals_stepping_and_oracle(n):
     # (1) fused rollout in three calls
     st_r, _ = fresh()
     ret = torch.zeros(n, dtype=torch.float64, device="cuda")
-    stats = torch.zeros(6, dtype=torch.float64, device="cuda")
+    stats = torch.zeros(15, dtype=torch.float64, device="cuda")
     for c in range(3):
         core.rollout(st_r, 61, ret, actions=_dev(acts[61 * c:61 * (c + 1)]), stats=stats)
     # (2) oracle, stopping every env at its terminal step
@@ -59,6 +59,8 @@ def test_rollout_equals_stepping_and_oracle(n):
     ret_ref = np.zeros(n)
     alive = np.ones(n, bool)
     n_steps = alerts = refused = 0
+    issued_days = [[] for _ in range(n)]   # day of summer of every issued alert, per env
+    streak_lens = []                        # lengths of streaks of issued alerts that ended
     # (3) the step kernel, frozen per env at its terminal step
     st_s, obs = fresh()
     reward = torch.zeros(n, device="cuda")
@@ -66,7 +68,14 @@ def test_rollout_equals_stepping_and_oracle(n):
     frozen = st_s.clone().view(2, n, 8)
     for k in range(total):
         before = ost["budget"] - ost["hist"].sum(axis=1)
+        t_before, streak_before = ost["t"].copy(), ost["streak"].copy()
         _, r, dn, rem, atb = orc.batch_step(store.feat, store.sig_code, weights.coef, ost, acts[k])
+        act_k = before - rem
+        for i in np.flatnonzero(alive):
+            if act_k[i]:
+                issued_days[i].append(int(t_before[i]))
+            elif streak_before[i] > 0:
+                streak_lens.append(int(streak_before[i]))
         ret_ref += np.where(alive, r, 0.0)
         n_steps += int(alive.sum())
         alerts += int(((before - rem) * alive).sum())
@@ -84,6 +93,24 @@ def test_rollout_equals_stepping_and_oracle(n):
     assert s["alerts"] == alerts and s["refused_at_budget"] == refused
     assert s["return_sum"] == pytest.approx(ret_ref[finished].sum(), rel=1e-9)
     assert s["return_sq_sum"] == pytest.approx((ret_ref[finished] ** 2).sum(), rel=1e-9)
+    # timing statistics (callbacks.py:63-74 on issued alerts)
+    all_days = np.array([d for days in issued_days for d in days], dtype=np.float64)
+    assert s["alert_day_sum"] == all_days.sum() and s["alert_day_sq_sum"] == (all_days ** 2).sum()
+    sl = np.array(streak_lens, dtype=np.float64)
+    assert s["streaks"] == len(sl) and s["streak_sum"] == sl.sum() and s["streak_sq_sum"] == (sl ** 2).sum()
+    # quantile days: only summers that ran from day 0 inside ONE call, i.e. those of at most 61 days here
+    a50 = a80 = a100 = cnt = 0
+    nd = store.n_days[idx["loc"], idx["year"]]
+    for i in range(n):
+        if finished[i] and nd[i] <= 61 and issued_days[i]:
+            d = np.array(issued_days[i])
+            tot = len(d)
+            cum = np.arange(1, tot + 1)
+            a50 += d[np.argmax(2 * cum >= tot)]
+            a80 += d[np.argmax(5 * cum >= 4 * tot)]
+            a100 += d[-1]
+            cnt += 1
+    assert (s["a50_sum"], s["a80_sum"], s["a100_sum"], s["a_count"]) == (a50, a80, a100, cnt)
     # a finished env is left alone by further rollouts
     snap = st_r.clone()
     core.rollout(st_r, 10, ret, actions=_dev(acts[:10]), stats=stats)
@@ -107,7 +134,8 @@ def test_rollout_hash_actions_match_host_stream(golden):
     ret_b, stats_b = env_b.rollout(actions=torch.from_numpy(bits))
     assert torch.equal(ret_a, ret_b)
     # counts are exact; the float sums go through atomics whose order is not fixed
-    assert torch.equal(stats_a[[0, 3, 4, 5]], stats_b[[0, 3, 4, 5]])
+    exact = [0, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
+    assert torch.equal(stats_a[exact], stats_b[exact]) and float(stats_a[14]) > 0
     assert torch.allclose(stats_a, stats_b, rtol=1e-12, atol=0)
     assert torch.equal(env_a._state, env_b._state)
     assert float(stats_a[0]) == n and float(stats_a[3]) == 153 * n

@@ -26,7 +26,7 @@ for n in (1, 31, 33, 257, 2049, 4100):
             core.step(state, a, obs, rew, term, rem, atb, variant=variant)
         mask = torch.from_numpy((rng.random(n) < 0.5).astype(np.uint8)).cuda()
         core.reset(state, obs, idx["loc"], idx["year"], idx["col"], idx["p"], mask=mask)
-        ret = torch.zeros(n, dtype=torch.float64, device="cuda"); stats = torch.zeros(6, dtype=torch.float64, device="cuda")
+        ret = torch.zeros(n, dtype=torch.float64, device="cuda"); stats = torch.zeros(15, dtype=torch.float64, device="cuda")
         acts = torch.from_numpy((rng.random((20, n)) < 0.5).astype(np.uint8)).cuda()
         core.rollout(state, 20, ret, actions=acts, stats=stats)
         core.rollout(state, 200, ret, seed=5, p_alert=0.4, stats=stats)

@@ -11,7 +11,7 @@ for n, loc in ((1<<20,'interleaved'), (1<<20,'sorted'), (1<<22,'interleaved'), (
     s = bench.index_streams(store, weights, n, 0, False, loc)
     idx = {k: torch.from_numpy(v).cuda() for k, v in s.items()}
     state = core.alloc_state(n); obs = torch.zeros((n,29), device='cuda')
-    ret = torch.zeros(n, dtype=torch.float64, device='cuda'); stats = torch.zeros(6, dtype=torch.float64, device='cuda')
+    ret = torch.zeros(n, dtype=torch.float64, device='cuda'); stats = torch.zeros(15, dtype=torch.float64, device='cuda')
     ts = []
     for it in range(4):
         core.reset(state, obs, idx['loc'], idx['year'], idx['coef_col'], idx['coef_idx'])

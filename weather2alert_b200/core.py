@@ -135,7 +135,7 @@ class HeatAlertCore:
         n = ep_return.numel()
         self._check_dev("state", state, torch.uint8, n * 16)
         self._check_dev("ep_return", ep_return, torch.float64, n)
-        self._check_dev("stats", stats, torch.float64, 6)
+        self._check_dev("stats", stats, torch.float64, 15)
         if actions is not None:
             self._check_dev("actions", actions, (torch.uint8, torch.bool), int(steps) * n)
         _lib.check(self._lib.w2a_rollout(self.ctx, self._stream(), n, int(steps), _ptr(actions), int(seed) & (2**64 - 1),

@@ -538,7 +538,7 @@ struct RolloutArgs {
   unsigned long long seed;
   unsigned threshold;      // P(action = 1) * 2^32 when actions == null
   double* ep_return;       // [n], +=
-  double* stats;           // [6], += (episodes, return_sum, return_sq_sum, steps, alerts, refused_at_budget)
+  double* stats;           // [kNumStats], += (see StatIndex)
   int n, steps;
 };
 
@@ -564,9 +564,18 @@ __host__ __device__ __forceinline__ unsigned rollout_hash(unsigned long long see
   return static_cast<unsigned>(z >> 32);
 }
 
+constexpr int kNumStats = 15;
+// index of each statistic in RolloutArgs::stats (weather2alert_b200/distributed.py: STAT_NAMES)
+enum StatIndex {
+  kStEpisodes = 0, kStReturnSum, kStReturnSq, kStSteps, kStAlerts, kStRefused,
+  kStAlertDaySum, kStAlertDaySq, kStStreaks, kStStreakSum, kStStreakSq,
+  kStA50Sum, kStA80Sum, kStA100Sum, kStACount
+};
+
 __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
-  __shared__ double s_stats[6];
-  if (threadIdx.x < 6) s_stats[threadIdx.x] = 0.0;
+  __shared__ double s_stats[kNumStats];
+  __shared__ unsigned char s_days[4][4][24];  // [warp][group][chunk]: issued-alert bits of the episode so far
+  if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int q = lane & 7;
@@ -574,7 +583,10 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int n_quads = (p.n + 3) >> 2;  // 4 envs per warp iteration
   const double2* const x_lane = reinterpret_cast<const double2*>(p.tb.x) + q;
-  double st_eps = 0.0, st_ret = 0.0, st_sq = 0.0, st_steps = 0.0, st_alerts = 0.0, st_ref = 0.0;
+  unsigned char* const my_days = s_days[threadIdx.x >> 5][g];
+  double acc[kNumStats];
+#pragma unroll
+  for (int i = 0; i < kNumStats; ++i) acc[i] = 0.0;
 
   for (int wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wq < n_quads; wq += warps_total) {
     const int e = wq * 4 + g;
@@ -589,6 +601,8 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
     int streak = (mv.y >> 8) & 0xff;
     unsigned win = (mv.y >> 16) & 0x3fffu;
     bool done = ((mv.y >> 30) & 1u) != 0 || !valid;
+    // the alert-timing quantiles need the whole summer: only for episodes that start in this call
+    const bool whole_episode = t == 0;
 
     // coefficient record -> float64 registers, once per episode
     const float4* wr = reinterpret_cast<const float4*>(p.tb.w + static_cast<size_t>(sv.y) * kWStride);
@@ -654,7 +668,8 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
         const int rem_after = rem - __popc(actm & ((2u << q) - 1u));
         const unsigned zeros = ~below & ((1u << q) - 1u);
         const int streak_q = zeros == 0u ? streak + q : q - 1 - (31 - __clz(zeros));
-        const int lag = (t + q) > 0 ? act : 0;
+        const int day = t + q;
+        const int lag = day > 0 ? act : 0;
         double zb = b2[0] + c_bias_b, ze = e2[0] + c_bias_e;
         zb = fma(static_cast<double>(lag), c_lag_b, zb);
         ze = fma(static_cast<double>(lag), c_lag_e, ze);
@@ -665,6 +680,15 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
         const double baseline = expit(zb);
         const double eff = act ? expit(ze) : 0.0;
         r_mine = kRewardScale * baseline * (1.0 - eff);
+        // timing statistics of this day: when alerts are issued, how long streaks of issued alerts last
+        if (act) {
+          acc[kStAlertDaySum] += day;
+          acc[kStAlertDaySq] += static_cast<double>(day) * day;
+        } else if (streak_q > 0) {  // a streak of streak_q issued alerts ended yesterday
+          acc[kStStreaks] += 1.0;
+          acc[kStStreakSum] += streak_q;
+          acc[kStStreakSq] += static_cast<double>(streak_q) * streak_q;
+        }
       }
       r_mine += __shfl_xor_sync(kFull, r_mine, 4);
       r_mine += __shfl_xor_sync(kFull, r_mine, 2);
@@ -674,6 +698,7 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
       if (nv > 0) {
         const unsigned vmask = (1u << nv) - 1u;  // nv <= 8
         const bool terminal = (t + nv) >= n_days;  // the chunk's last day is the episode's last
+        if (whole_episode && q == 0) my_days[t >> 3] = static_cast<unsigned char>(actm & vmask);  // t is a multiple of 8 here
         // the streak is not updated on the terminal day
         const int ns = terminal ? nv - 1 : nv;
         const unsigned sm = (1u << ns) - 1u;
@@ -685,9 +710,9 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
         t = terminal ? n_days - 1 : t + nv;
         k += nv;
         if (q == 0) {
-          st_steps += nv;
-          st_alerts += __popc(actm & vmask);
-          st_ref += __popc(refm & vmask);
+          acc[kStSteps] += nv;
+          acc[kStAlerts] += __popc(actm & vmask);
+          acc[kStRefused] += __popc(refm & vmask);
         }
         if (terminal) done = true;
       }
@@ -699,24 +724,43 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
                                static_cast<unsigned>(t) | (static_cast<unsigned>(streak) << 8) | (win << 16) |
                                    ((done ? 1u : 0u) << 30));
       if (done) {
-        st_eps += 1.0;
-        st_ret += total;
-        st_sq += total * total;
+        acc[kStEpisodes] += 1.0;
+        acc[kStReturnSum] += total;
+        acc[kStReturnSq] += total * total;
+        if (whole_episode) {
+          // day by which 50 % / 80 % / 100 % of the summer's alerts had been issued (callbacks.py:47-57)
+          const int n_chunks = (n_days + 7) >> 3;
+          int issued = 0;
+          for (int c = 0; c < n_chunks; ++c) issued += __popc(static_cast<unsigned>(my_days[c]));
+          if (issued > 0) {
+            int cum = 0, d50 = -1, d80 = -1, d100 = -1;
+            for (int d = 0; d < n_days && d100 < 0; ++d) {
+              cum += (my_days[d >> 3] >> (d & 7)) & 1;
+              if (d50 < 0 && 2 * cum >= issued) d50 = d;
+              if (d80 < 0 && 5 * cum >= 4 * issued) d80 = d;
+              if (cum == issued) d100 = d;
+            }
+            acc[kStA50Sum] += d50;
+            acc[kStA80Sum] += d80;
+            acc[kStA100Sum] += d100;
+            acc[kStACount] += 1.0;
+          }
+        }
       }
     }
+    __syncwarp();
   }
-  // ---- statistics: lanes -> block (shared atomics) -> one global atomic per block and field ---
+  // ---- statistics: lanes -> warp (shuffles) -> block (shared atomics) -> one global atomic per block and field
   if (p.stats) {
-    if (q == 0) {
-      atomicAdd(&s_stats[0], st_eps);
-      atomicAdd(&s_stats[1], st_ret);
-      atomicAdd(&s_stats[2], st_sq);
-      atomicAdd(&s_stats[3], st_steps);
-      atomicAdd(&s_stats[4], st_alerts);
-      atomicAdd(&s_stats[5], st_ref);
+#pragma unroll
+    for (int i = 0; i < kNumStats; ++i) {
+      double v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+      if (lane == 0 && v != 0.0) atomicAdd(&s_stats[i], v);
     }
     __syncthreads();
-    if (threadIdx.x < 6 && s_stats[threadIdx.x] != 0.0) atomicAdd(p.stats + threadIdx.x, s_stats[threadIdx.x]);
+    if (threadIdx.x < kNumStats && s_stats[threadIdx.x] != 0.0) atomicAdd(p.stats + threadIdx.x, s_stats[threadIdx.x]);
   }
 }
 

@@ -13,7 +13,9 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-STAT_NAMES = ("episodes", "return_sum", "return_sq_sum", "steps", "alerts", "refused_at_budget")
+STAT_NAMES = ("episodes", "return_sum", "return_sq_sum", "steps", "alerts", "refused_at_budget",
+              "alert_day_sum", "alert_day_sq_sum", "streaks", "streak_sum", "streak_sq_sum",
+              "a50_sum", "a80_sum", "a100_sum", "a_count")
 N_STATS = len(STAT_NAMES)
 
 
@@ -43,7 +45,7 @@ class RolloutStats:
         upd = torch.stack([done.sum().double(), fin.sum(), (fin * fin).sum(),
                            torch.tensor(float(reward.numel()), dtype=torch.float64, device=reward.device),
                            (a & ~atb).sum().double(), (a & atb).sum().double()])
-        self.totals += upd
+        self.totals[:6] += upd  # the timing statistics (6..14) are produced by the rollout kernel only
         self.ep_return.masked_fill_(done, 0.0)
 
     def reduce(self, group=None) -> torch.Tensor:
@@ -65,8 +67,20 @@ def summarize(stats: torch.Tensor) -> dict:
     n_ep, n_steps = max(s["episodes"], 1.0), max(s["steps"], 1.0)
     mean = s["return_sum"] / n_ep
     var = max(s["return_sq_sum"] / n_ep - mean * mean, 0.0)
-    return {**s, "mean_return": mean, "std_return": var ** 0.5,
-            "alert_freq": s["alerts"] / n_steps, "over_budget_freq": s["refused_at_budget"] / n_steps}
+    out = {**s, "mean_return": mean, "std_return": var ** 0.5,
+           "alert_freq": s["alerts"] / n_steps, "over_budget_freq": s["refused_at_budget"] / n_steps}
+
+    def mean_std(total, sq, count):
+        if count <= 0:
+            return float("nan"), float("nan")
+        m = total / count
+        return m, max(sq / count - m * m, 0.0) ** 0.5
+
+    out["average_t_alerts"], out["stdev_t_alerts"] = mean_std(s["alert_day_sum"], s["alert_day_sq_sum"], s["alerts"])
+    out["average_streak"], out["stdev_streak"] = mean_std(s["streak_sum"], s["streak_sq_sum"], s["streaks"])
+    for k in ("a50", "a80", "a100"):
+        out[f"alert_t_{k[1:]}%"] = s[f"{k}_sum"] / s["a_count"] if s["a_count"] > 0 else float("nan")
+    return out
 
 
 def rollout_action_bits(seed: int, envs, steps, p_alert: float):

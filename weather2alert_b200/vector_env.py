@@ -277,7 +277,7 @@ class HeatAlertVectorEnv:
             if actions.shape != (steps, self.num_envs):
                 raise ValueError(f"actions must have shape ({steps}, {self.num_envs})")
         if stats is None:
-            stats = torch.zeros(6, dtype=torch.float64, device=self.device)
+            stats = torch.zeros(15, dtype=torch.float64, device=self.device)
         ep_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
         self.core.rollout(self._state, steps, ep_return, actions=actions, seed=seed, p_alert=p_alert, stats=stats)
         self._step_no += steps
