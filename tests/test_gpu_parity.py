@@ -259,3 +259,43 @@ def test_abi_error_paths():
     assert lib.w2a_step_host(ctx, None, None, None, None, None, None) == -3
     assert lib.w2a_set_coefs(ctx, None, 1, 1) == -1
     assert lib.w2a_destroy(ctx) == 0
+
+
+@pytest.mark.parametrize("S,Y,P,T", [(1, 1, 1, 153), (3, 2, 5, 7), (2, 1, 2, 255)])
+def test_degenerate_table_shapes(S, Y, P, T):
+    """One county / one year / one posterior sample, very short and maximum-length summers."""
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200 import schema, synthetic
+    from weather2alert_b200.core import HeatAlertCore
+    from weather2alert_b200.store import FeatureStore
+
+    rng = np.random.default_rng(S * 100 + T)
+    fips, zones = synthetic.synthetic_counties(S, seed=1)
+    base = synthetic.make_store(fips, list(range(2006, 2006 + Y)), seed=2, zones=zones)
+    if T != schema.MAX_DAYS:  # rebuild with a different day count
+        reps = -(-T // schema.MAX_DAYS)
+        feat = np.tile(base.feat, (1, 1, reps, 1))[:, :, :T].copy()
+        sig = np.tile(base.sig_code, (1, 1, reps))[:, :, :T].copy()
+        store = FeatureStore(fips=base.fips, years=base.years, n_days=np.full((S, Y), T, np.uint8), feat=feat,
+                             sig_code=sig, sig_labels=base.sig_labels, conf_fips=base.conf_fips, conf_zone=base.conf_zone)
+    else:
+        store = base
+    weights = synthetic.make_weights(fips, P, seed=3)
+    core = HeatAlertCore(store, weights, "cuda:0")
+    n = 70
+    idx = {k: v.astype(np.int32) for k, v in dict(loc=rng.integers(0, S, n), year=rng.integers(0, Y, n),
+                                                    coef_col=rng.integers(0, S, n), coef_idx=rng.integers(0, P, n)).items()}
+    state = core.alloc_state(n)
+    obs = torch.zeros((n, 29), device="cuda")
+    core.reset(state, obs, *(_dev(idx[k]) for k in ("loc", "year", "coef_col", "coef_idx")))
+    st, o_ref = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"], idx["coef_col"], idx["coef_idx"])
+    assert_obs_equal(obs.cpu().numpy(), o_ref)
+    reward = torch.zeros(n, device="cuda")
+    term = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    for i in range(min(T + 3, 40) if T < 200 else T + 2):
+        act = (rng.random(n) < 0.5).astype(np.uint8)
+        core.step(state, _dev(act), obs, reward, term, variant=2 if i % 2 else 1)
+        o_ref, r_ref, d_ref, _, _ = orc.batch_step(store.feat, store.sig_code, weights.coef, st, act)
+        assert_obs_equal(obs.cpu().numpy(), o_ref, f"step {i}")
+        np.testing.assert_allclose(reward.cpu().numpy(), r_ref, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+        np.testing.assert_array_equal(term.cpu().numpy().astype(bool), d_ref)

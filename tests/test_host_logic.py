@@ -1,5 +1,4 @@
 """CPU tests of the host side: packing, climate groups, sampling order, ABI surface."""
-import ctypes
 import os
 import re
 

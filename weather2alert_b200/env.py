@@ -20,7 +20,7 @@ from typing import Literal
 
 import numpy as np
 
-from . import _lib, schema
+from . import schema
 from ._gym import Env, spaces
 from .core import HeatAlertCore
 from .loading import load_store, load_weights
