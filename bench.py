@@ -205,7 +205,8 @@ def run_ours(args):
     # Replay one CUDA graph per summer (T step launches + the reset) instead of T+1 host launches:
     # small batches are launch-latency bound and even at 2^20 envs the Python-side
     # launch loop costs a few per cent.
-    use_graph = not args.no_graph
+    # graph replays cover whole summers; any other --steps/--warmup is honoured exactly with host launches
+    use_graph = (not args.no_graph) and args.steps % T == 0 and args.warmup % T == 0
     graph = None
     if use_graph:
         do_reset()
@@ -226,8 +227,6 @@ def run_ours(args):
                 step(actions[i])
             return k
 
-        K = max(T, (K // T) * T)  # whole summers, so that the timed region is graph replays only
-        W = max(T, (W // T) * T)
 
     do_reset()
     t = run_steps(W, 0)

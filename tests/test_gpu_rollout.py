@@ -139,3 +139,41 @@ def test_rollout_hash_actions_match_host_stream(golden):
     assert torch.allclose(stats_a, stats_b, rtol=1e-12, atol=0)
     assert torch.equal(env_a._state, env_b._state)
     assert float(stats_a[0]) == n and float(stats_a[3]) == 153 * n
+
+
+def test_rollout_at_baseline_size_matches_stepping():
+    """2**20 envs (BASELINE configs[2] size), a full summer: the fused rollout leaves the same state
+    bytes as 153 step launches and its float64 returns equal the sum of the stepped float32 rewards."""
+    from weather2alert_b200 import synthetic
+    from weather2alert_b200.core import HeatAlertCore
+
+    n, S, Y, P = 1 << 20, 64, 4, 32
+    fips, zones = synthetic.synthetic_counties(S, seed=5)
+    store = synthetic.make_store(fips, list(range(2006, 2006 + Y)), seed=6, zones=zones)
+    core = HeatAlertCore(store, synthetic.make_weights(fips, P, seed=7), "cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ri = lambda hi: torch.randint(0, hi, (n,), generator=g, device="cuda", dtype=torch.int32)  # noqa: E731
+    loc, year, cidx, budget = ri(S), ri(Y), ri(P), ri(12)
+    acts = (torch.rand((153, n), generator=g, device="cuda") < 0.3).to(torch.uint8)
+
+    def fresh():
+        st = core.alloc_state(n)
+        obs = torch.zeros((n, 29), device="cuda")
+        core.reset(st, obs, loc, year, loc, cidx, budget=budget)
+        return st, obs
+
+    st_r, _ = fresh()
+    ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    stats = torch.zeros(15, dtype=torch.float64, device="cuda")
+    core.rollout(st_r, 153, ret, actions=acts, stats=stats)
+    st_s, obs = fresh()
+    reward = torch.zeros(n, device="cuda")
+    term = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    total = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for k in range(153):
+        core.step(st_s, acts[k], obs, reward, term)
+        total += reward.double()
+    assert bool(term.all()) and torch.equal(st_r, st_s)
+    assert torch.allclose(ret, total, rtol=1e-6, atol=0)  # float32 rounding of each stepped reward
+    assert float(stats[0]) == n and float(stats[3]) == 153 * n
+    assert float(stats[1]) == pytest.approx(float(ret.sum()), rel=1e-9)
