@@ -296,6 +296,45 @@ def run_ours(args):
                     "mean_return": ro_sum["mean_return"],
                     "same_returns_as_stepping": bool(abs(ro_sum["mean_return"] - stats["mean_return"]) <= 1e-6 * abs(stats["mean_return"]))}
 
+    # ---- policy in the loop (BASELINE configs[4] style): a small torch MLP policy on the observations and
+    # the step kernel, a whole summer + reset captured in ONE CUDA graph (HeatAlertVectorEnv.graphed_rollout)
+    policy_info = None
+    if not args.no_e2e:
+        try:
+            from weather2alert_b200.vector_env import HeatAlertVectorEnv
+
+            venv = HeatAlertVectorEnv(n, core=core, seed=1234 + rank, similar_climate_counties=wl["augment"],
+                                      sort_episodes=(args.locality == "sorted"))
+            venv.reset()
+            gp = torch.Generator(device=dev).manual_seed(5)
+            pw1 = torch.randn(29, 64, generator=gp, device=dev) * 0.3
+            pw2 = torch.randn(64, generator=gp, device=dev) * 0.3
+
+            def policy(o):
+                return (torch.relu(torch.nan_to_num(o) @ pw1) @ pw2) > 0.0
+
+            roll = venv.graphed_rollout(policy, reset_at_end=True)
+            roll.replay()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            p0.record()
+            for _ in range(3):
+                roll.replay()
+            p1.record()
+            torch.cuda.synchronize()
+            p_t = torch.tensor([p0.elapsed_time(p1) / 3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(p_t, op=dist.ReduceOp.MAX)
+            policy_info = {"value": n * world * roll.steps / (float(p_t.item()) * 1e-3), "unit": UNIT,
+                           "ms_per_summer": float(p_t.item()), "steps_per_summer": roll.steps,
+                           "policy": "torch MLP 29-64-1 (fp32 matmuls) on the observation tensor, deterministic threshold",
+                           "mode": "policy forward + step kernel x 153 + reset in one CUDA graph"}
+            del roll, venv
+        except Exception as exc:  # an extra: never let it take the headline line down
+            policy_info = {"error": repr(exc)[:300]}
+
     # ---- end to end through the host-buffer C entry points: `e2e` ---------------------------------
     e2e = None
     if not args.no_e2e:
@@ -380,6 +419,7 @@ def run_ours(args):
         "return_stats": {**stats, "reduced_over": world},
         "rollout": rollout_info,
         "single_env": single,
+        "policy_in_loop": policy_info,
     }
     traffic_file = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(traffic_file):

@@ -165,3 +165,38 @@ def test_sort_episodes_is_a_permutation_of_the_same_draws(golden):
     kb = torch.stack([b._idx[k] for k in ("loc", "coef_col", "coef_idx", "year")], 1).cpu().numpy()
     assert sorted(map(tuple, ka)) == list(map(tuple, kb))  # same multiset, lexicographic order
     assert torch.equal(b._list_idx, b._idx["list_idx"])
+
+
+def test_graphed_policy_rollout_equals_eager_loop():
+    """policy(obs) -> step, 153 times, captured in one CUDA graph == the same loop launched eagerly."""
+    from weather2alert_b200 import HeatAlertVectorEnv, synthetic
+
+    fips, zones = synthetic.synthetic_counties(20, seed=2)
+    store = synthetic.make_store(fips, [2006, 2007], seed=3, zones=zones)
+    weights = synthetic.make_weights(fips, 8, seed=4)
+    n = 3000
+    w_pol = torch.randn(29, device="cuda") * 0.5
+
+    def policy(obs):  # deterministic logistic policy on the observation (NaN significance -> 0)
+        return (torch.nan_to_num(obs) @ w_pol) > 0.3
+
+    kw = dict(weights=weights, store=store, seed=12, budget=6)
+    eager = HeatAlertVectorEnv(n, autoreset=False, **kw)
+    obs, _ = eager.reset()
+    ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for _ in range(153):
+        obs, r, term, _, _ = eager.step(policy(obs))
+        ret += r
+    assert bool(term.all())
+
+    graphed = HeatAlertVectorEnv(n, **kw)
+    graphed.reset()
+    roll = graphed.graphed_rollout(policy, reset_at_end=True)
+    got = roll.replay().clone()
+    assert torch.equal(got, ret)
+    # the captured reset started a new summer: the first observation is a fresh day-0 row
+    assert bool((graphed._obs[:, 17] == 0).all()) and graphed._step_no == 153
+    second = roll.replay().clone()
+    assert not torch.equal(second, got) and bool(torch.isfinite(second).all())
+    with pytest.raises(ValueError):
+        graphed.graphed_rollout(policy, steps=154)

@@ -34,6 +34,8 @@ class RolloutStats:
     def __init__(self, num_envs: int, device):
         self.ep_return = torch.zeros(num_envs, dtype=torch.float64, device=device)
         self.totals = torch.zeros(N_STATS, dtype=torch.float64, device=device)
+        # a device constant, so that `update` creates no tensor from host data (CUDA-graph capturable)
+        self._n = torch.full((), float(num_envs), dtype=torch.float64, device=device)
 
     def update(self, actions, reward, terminated, at_budget):
         """One step: `actions` any integer/bool dtype, `at_budget` the pre-action flag."""
@@ -42,8 +44,7 @@ class RolloutStats:
         self.ep_return += reward.double()
         done = terminated.bool()
         fin = torch.where(done, self.ep_return, torch.zeros_like(self.ep_return))
-        upd = torch.stack([done.sum().double(), fin.sum(), (fin * fin).sum(),
-                           torch.tensor(float(reward.numel()), dtype=torch.float64, device=reward.device),
+        upd = torch.stack([done.sum().double(), fin.sum(), (fin * fin).sum(), self._n,
                            (a & ~atb).sum().double(), (a & atb).sum().double()])
         self.totals[:6] += upd  # the timing statistics (6..14) are produced by the rollout kernel only
         self.ep_return.masked_fill_(done, 0.0)

@@ -180,8 +180,14 @@ class HeatAlertVectorEnv:
         if budget is not None or o.get("sample_budget", False):
             if budget is None:
                 b = self.core.budget0[(loc * self.core.Y + year)].long()
+            elif np.ndim(budget) == 0:
+                b = torch.full((n,), int(budget), dtype=torch.int64, device=dev)  # a fill kernel: graph capturable
             else:
-                b = torch.as_tensor(np.broadcast_to(np.asarray(budget, dtype=np.int64), (n,)).copy()).to(dev)
+                key = id(budget)
+                if getattr(self, "_budget_cache", (None, None))[0] != key:  # uploaded once, reused by captured resets
+                    self._budget_cache = (key, torch.as_tensor(
+                        np.ascontiguousarray(np.broadcast_to(np.asarray(budget, dtype=np.int64), (n,)))).to(dev))
+                b = self._budget_cache[1]
             if o.get("sample_budget", False):  # env.py:172-177, per env, without the sticky compounding (Q8)
                 u = torch.rand(n, generator=self._gen, device=dev, dtype=torch.float64)
                 if o.get("sample_budget_type", "less_than") == "less_than":
@@ -283,6 +289,28 @@ class HeatAlertVectorEnv:
         self._step_no += steps
         return ep_return, stats
 
+    # ---- policy in the loop, replayed as one CUDA graph ------------------------------------------------
+    def graphed_rollout(self, policy, steps: int | None = None, reset_at_end: bool = False):
+        """Capture `steps` iterations of ``actions = policy(obs); env.step(actions)`` into ONE CUDA
+        graph (the policy's torch kernels and the step kernel, no host work in between) and return
+        a `GraphedRollout`; every `replay()` advances all envs by `steps` steps and returns the
+        float64 return of each env over those steps.
+
+        `policy` maps the float32 ``[N, 29]`` observation tensor to an ``[N]`` action tensor
+        (bool / integer; non-zero = alert) using capturable torch ops only.  The capture must
+        not run past the end of an episode; with ``reset_at_end=True`` (summers of equal length,
+        `steps` = days left) the reset of all envs is captured too, so that `replay()` can be
+        called forever: one replay = one summer."""
+        if self._next_term is None:
+            raise RuntimeError("call reset() before graphed_rollout()")
+        left = self._next_term - self._step_no
+        steps = left if steps is None else int(steps)
+        if steps < 1 or steps > left or self._term_at is not None and steps > left:
+            raise ValueError(f"graphed_rollout: steps={steps} must be in [1, {left}] (days left in the episodes)")
+        if reset_at_end and (self._uniform_days is None or steps != left or "index_streams" in self._reset_opts):
+            raise ValueError("reset_at_end needs summers of equal length, steps == days left and device-side sampling")
+        return GraphedRollout(self, policy, steps, reset_at_end)
+
     def _infos(self):
         return {"remaining_budget": self._rem, "at_budget": self._atb, "location_index": self._list_idx}
 
@@ -305,3 +333,64 @@ class HeatAlertVectorEnv:
 
     def close(self):
         self.core = None
+
+
+class GraphedRollout:
+    """One CUDA graph of `steps` x (policy forward + step kernel); see `HeatAlertVectorEnv.graphed_rollout`."""
+
+    def __init__(self, env: HeatAlertVectorEnv, policy, steps: int, reset_at_end: bool):
+        self.env, self.steps, self.reset_at_end = env, steps, reset_at_end
+        n, dev = env.num_envs, env.device
+        self.returns = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._act = torch.zeros(n, dtype=torch.uint8, device=dev)
+        step = env.core.bind_step(env._state, env._obs, env._reward, env._term.view(torch.uint8), env._rem,
+                                  env._atb.view(torch.uint8), variant=env.step_variant, action_dtype=torch.uint8)
+
+        def body():
+            self.returns.zero_()
+            for _ in range(steps):
+                a = policy(env._obs)
+                self._act.copy_(a.reshape(n).ne(0) if a.dtype != torch.bool else a.reshape(n))
+                step(self._act)
+                if env.stats is not None:
+                    env.stats.update(self._act, env._reward, env._term, env._atb)
+                self.returns.add_(env._reward)
+            if reset_at_end:
+                s = env._draw()
+                env._idx = s
+                env.core.reset(env._state, env._obs, s["loc"], s["year"], s["coef_col"], s["coef_idx"],
+                               budget=s.get("budget"), remaining=env._rem)
+                env._list_idx.copy_(s["list_idx"])
+                env._atb.zero_()
+
+        # warm up on a side stream (lazy initialisation of torch kernels and of the launch tables), on
+        # a copy of the env state so that the capture starts from where the env is now
+        snap = (env._state.clone(), env._obs.clone(), env._gen.get_state(), env._list_idx.clone())
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        env._state.copy_(snap[0])
+        env._obs.copy_(snap[1])
+        env._gen.set_state(snap[2])
+        env._list_idx = snap[3]
+        if env.stats is not None:
+            env.stats.totals.zero_()
+            env.stats.ep_return.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        self.graph.register_generator_state(env._gen)
+        with torch.cuda.graph(self.graph):
+            body()
+        # the capture itself does not execute anything: the env is still where it was
+
+    def replay(self) -> torch.Tensor:
+        env = self.env
+        if not self.reset_at_end and env._step_no + self.steps > env._next_term:
+            raise RuntimeError("replay would run past the end of the episodes; reset() the env first")
+        self.graph.replay()
+        env._step_no += self.steps
+        if self.reset_at_end:
+            env._next_term = env._step_no + env._uniform_days
+        return self.returns
