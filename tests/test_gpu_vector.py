@@ -200,3 +200,31 @@ def test_graphed_policy_rollout_equals_eager_loop():
     assert not torch.equal(second, got) and bool(torch.isfinite(second).all())
     with pytest.raises(ValueError):
         graphed.graphed_rollout(policy, steps=154)
+
+
+def test_reference_rng_reset_equals_independent_single_envs(golden):
+    """reset(seed=s, options={'reference_rng': True}): env i == HeatAlertEnv().reset(seed=s+i) -- the
+    seeding rule of gymnasium.vector.SyncVectorEnv -- including augmentation and budget sampling."""
+    from weather2alert_b200 import HeatAlertEnv, HeatAlertVectorEnv
+
+    store, weights = golden.store(), golden.weights("std")
+    n, seed = 12, 4321
+    opts = dict(reference_rng=True, similar_climate_counties=True, sample_budget=True, sample_budget_type="centered")
+    venv = HeatAlertVectorEnv(n, weights=weights, store=store, autoreset=False, budget=6)
+    obs, info = venv.reset(seed=seed, options=opts)
+    singles = []
+    for i in range(n):
+        e = HeatAlertEnv(weights=weights, store=store, budget=6)
+        o, inf = e.reset(seed=seed + i, similar_climate_counties=True, sample_budget=True, sample_budget_type="centered")
+        np.testing.assert_array_equal(obs[i].cpu().numpy().view(np.int32), o.view(np.int32))
+        assert inf["remaining_budget"] == int(info["remaining_budget"][i])
+        assert weights.fips_list.index(str(inf["location"])) == int(info["location_index"][i])
+        singles.append(e)
+    rng = np.random.default_rng(0)
+    for _ in range(25):
+        a = rng.integers(0, 2, n)
+        obs, rew, term, _, info = venv.step(torch.from_numpy(a).cuda())
+        for i, e in enumerate(singles):
+            o, r, d, _, inf = e.step(int(a[i]))
+            np.testing.assert_array_equal(obs[i].cpu().numpy().view(np.int32), o.view(np.int32))
+            assert r == float(rew[i]) and d == bool(term[i]) and inf["at_budget"] == bool(info["at_budget"][i])

@@ -146,6 +146,30 @@ class HeatAlertVectorEnv:
             return s
         augment = o.get("similar_climate_counties", self.similar_climate_counties)
         location = o.get("location")
+        if o.get("reference_rng", False):
+            # what gymnasium.vector.SyncVectorEnv([HeatAlertEnv]*N).reset(seed=s) does: env i seeds its
+            # own PCG64 with s + i and draws in the reference order (env.py:143-177).  Host loop: for
+            # parity and small batches.
+            base_seed = o["reference_seed"]
+            locs = location if isinstance(location, (list, tuple, np.ndarray)) else [location] * n
+            rows, budgets = [], []
+            for i in range(n):
+                rng = np.random.default_rng(int(base_seed) + i)
+                d = sp.draw_reference(rng, locs[i], augment)
+                b = o.get("budget", self.budget)
+                b = int(self.store.budget0[d["s"], d["y"]]) if b is None else int(np.asarray(b).reshape(-1)[i % np.size(b)])
+                if o.get("sample_budget", False):  # env.py:172-177
+                    if o.get("sample_budget_type", "less_than") == "less_than":
+                        b = int(rng.integers(0, b + 1))
+                    else:
+                        b = int(rng.integers(0.5 * b, 1.5 * b + 1))
+                rows.append((d["s"], d["y"], d["location_index"], d["coef_index"], sp.fips_list.index(d["info_location"])))
+                budgets.append(b)
+            arr = np.array(rows, dtype=np.int32).reshape(n, 5)
+            s = {k: torch.from_numpy(np.ascontiguousarray(arr[:, j])).to(dev)
+                 for j, k in enumerate(("loc", "year", "coef_col", "coef_idx", "list_idx"))}
+            s["budget"] = torch.from_numpy(np.array(budgets, dtype=np.int32)).to(dev)
+            return s
         if location is None:
             list_idx = self._randint(len(sp.fips_list), n)  # env.py:151-152
         elif isinstance(location, str):
@@ -201,12 +225,18 @@ class HeatAlertVectorEnv:
     # ---- reset --------------------------------------------------------------------------------
     def reset(self, *, seed: int | None = None, options: dict | None = None):
         """`options` keys: `location` (FIPS, or a sequence of N), `similar_climate_counties`,
-        `budget` (int or sequence), `sample_budget`, `sample_budget_type`, or `index_streams`
-        (dict of int arrays `loc`, `year`, `coef_col`, `coef_idx`[, `budget`, `list_idx`])."""
+        `budget` (int or sequence), `sample_budget`, `sample_budget_type`, `reference_rng` (True: env i
+        draws from its own ``default_rng(seed + i)`` in the reference's order, like a gymnasium
+        SyncVectorEnv of reference envs), or `index_streams` (dict of int arrays `loc`, `year`,
+        `coef_col`, `coef_idx`[, `budget`, `list_idx`])."""
         if seed is not None:
             self._gen.manual_seed(int(seed))
             self._host_rng = np.random.default_rng(seed)
         self._reset_opts = dict(options or {})
+        if self._reset_opts.get("reference_rng", False):
+            if seed is None:
+                raise ValueError("options['reference_rng'] needs reset(seed=...)")
+            self._reset_opts["reference_seed"] = int(seed)
         self._step_no = 0
         self._reset_subset(None)
         return self._obs, self._infos()
