@@ -92,6 +92,25 @@ def index_streams(store, weights, n, rank, augment, locality="interleaved"):
     return s
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPU cores next to its GPU (NVML's ideal affinity), so that the pinned host
+    buffers of the e2e path are first-touched on that NUMA node and PCIe DMA does not cross sockets."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            log(f"[gpu {index}] bound to {len(cpus)} cores of its NUMA node")
+    except Exception as exc:  # pragma: no cover - best effort
+        log(f"[gpu {index}] no NUMA binding: {exc}")
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -159,6 +178,7 @@ def run_ours(args):
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one process per GPU)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
