@@ -50,9 +50,9 @@ extern "C" {
 #define W2A_ACT_I64 2
 
 /* kernel variant for w2a_step */
-#define W2A_STEP_AUTO 0
+#define W2A_STEP_AUTO 0   /* THREAD below 2048 envs, COOP from there on */
 #define W2A_STEP_THREAD 1 /* one thread per env (small batches, reference kernel) */
-#define W2A_STEP_COOP 2   /* 8 lanes per env, coalesced gathers + warp-shuffle reduction */
+#define W2A_STEP_COOP 2   /* 8 lanes per env: whole-line gathers, float64 fold in shared memory, TMA obs store */
 
 /* per-env budget value meaning "use the episode's historical budget"
  * (env.py:167-170: `self.ep["remaining_budget"].iloc[0]`). */
