@@ -1,0 +1,62 @@
+"""Copy the evidence of tools/gpu_final_profile.sh from gpurun_out/final into profiles/<round>/ and refresh profiles/traffic.json."""
+import collections
+import csv
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+src, dst = os.path.join(REPO, "gpurun_out", "final"), os.path.join(REPO, "profiles", rnd)
+os.makedirs(dst, exist_ok=True)
+rep = os.path.join(src, "prof_step_coop.ncu-rep")
+
+
+def ncu(page):
+    return subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+
+
+open(os.path.join(dst, "final_step_coop_raw.csv"), "w").write(ncu("raw"))
+open("/tmp/src_final.csv", "w").write(ncu("source"))
+ops = subprocess.run([sys.executable, os.path.join(REPO, "tools", "ncu_ops.py"), "/tmp/src_final.csv", "1048576"],
+                     capture_output=True, text=True).stdout
+open(os.path.join(dst, "final_step_coop_per_opcode.txt"), "w").write(ops)
+det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
+open(os.path.join(dst, "final_step_coop_details.txt"), "w").write("\n".join(l for l in det.splitlines() if l.strip())[:20000])
+shutil.copy(os.path.join(src, "launches.csv"), os.path.join(dst, "final_launches.csv"))
+for f in os.listdir(src):
+    if f.startswith("bench_") and f.endswith(".json"):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, "final_" + f))
+rows = list(csv.reader(open(os.path.join(dst, "final_step_coop_raw.csv"))))
+hdr, units, r = rows[0], rows[1], rows[2]
+g = lambda k: float(r[hdr.index(k)])  # noqa: E731
+mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[units[hdr.index("dram__bytes_read.sum")]]
+rd, wr = g("dram__bytes_read.sum") * mult, g("dram__bytes_write.sum") * mult
+json.dump({"workload": "cfg3_1m", "envs": 1048576, "kernel": "step_coop_kernel", "dram_bytes_per_launch": rd + wr,
+           "dram_bytes_read": rd, "dram_bytes_written": wr,
+           "source": f"profiles/{rnd}/final_step_coop_raw.csv (ncu --set full, one launch)"},
+          open(os.path.join(REPO, "profiles", "traffic.json"), "w"), indent=1)
+for k in ("gpu__time_duration.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+          "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+          "lts__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+          "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct"):
+    print(k, r[hdr.index(k)], units[hdr.index(k)])
+print("dram read/write MB", rd / 1e6, wr / 1e6)
+lrows = list(csv.reader(open(os.path.join(dst, "final_launches.csv"))))
+hi = next(i for i, x in enumerate(lrows) if x and x[0] == "ID")
+kn, mv = lrows[hi].index("Kernel Name"), lrows[hi].index("Metric Value")
+agg = collections.defaultdict(lambda: [0, 0.0])
+for x in lrows[hi + 1:]:
+    if len(x) > mv:
+        agg[x[kn].split("(")[0][-50:]][0] += 1
+        agg[x[kn].split("(")[0][-50:]][1] += float(x[mv])
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:4]:
+    print(v[0], "x", k, round(v[1] / v[0] / 1e3, 1), "us avg")
+for f in sorted(os.listdir(dst)):
+    if f.startswith("final_bench_") and f.endswith(".json"):
+        d = json.loads(open(os.path.join(dst, f)).read().strip().splitlines()[-1])
+        print(f, "%.3e" % d["value"], d.get("ms_per_step"), (d.get("roofline") or {}).get("frac"),
+              (d.get("roofline_canonical_466B") or {}).get("frac"), (d.get("e2e") or {}).get("value"),
+              (d.get("rollout") or {}).get("value"), (d.get("policy_in_loop") or {}).get("value"))

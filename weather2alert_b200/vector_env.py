@@ -95,6 +95,8 @@ class HeatAlertVectorEnv:
         # every (county of the weights, valid year) exists -> device draws cannot hit a missing episode
         self._all_episodes_exist = bool(ok_c.all() and ok_y.all() and (sub > 0).all())
         self._uniform_days = int(sub.flat[0]) if sub.size and (sub == sub.flat[0]).all() else None
+        # every county of the weights has a non-empty similar-county list -> augmented draws cannot fail either
+        self._augment_safe = bool((sp.n_similar > 0).all())
         self._n_days_dev = core.n_days  # uint8 [S*Y]
 
         self._state = core.alloc_state(n)
@@ -186,7 +188,7 @@ class HeatAlertVectorEnv:
             coef_col = list_idx  # env.py:121
         year = self._valid_year_idx[self._randint(len(sp.valid_years), n)]  # env.py:125
         coef_idx = self._randint(sp.n_samples, n)  # env.py:160
-        if not self._all_episodes_exist or augment:
+        if not self._all_episodes_exist or (augment and not self._augment_safe):
             bad = (loc < 0) | (year < 0)
             if augment:
                 bad |= self._n_similar[list_idx] <= 0
@@ -337,8 +339,13 @@ class HeatAlertVectorEnv:
         steps = left if steps is None else int(steps)
         if steps < 1 or steps > left or self._term_at is not None and steps > left:
             raise ValueError(f"graphed_rollout: steps={steps} must be in [1, {left}] (days left in the episodes)")
-        if reset_at_end and (self._uniform_days is None or steps != left or "index_streams" in self._reset_opts):
+        if reset_at_end and (self._uniform_days is None or steps != left or "index_streams" in self._reset_opts
+                             or self._reset_opts.get("reference_rng", False)):
             raise ValueError("reset_at_end needs summers of equal length, steps == days left and device-side sampling")
+        augment = self._reset_opts.get("similar_climate_counties", self.similar_climate_counties)
+        if reset_at_end and (not self._all_episodes_exist or (augment and not self._augment_safe)):
+            raise ValueError("reset_at_end: some (county, year) episodes or similar-county lists are missing, so a "
+                             "reset needs a host-side check and cannot be captured")
         return GraphedRollout(self, policy, steps, reset_at_end)
 
     def _infos(self):
