@@ -553,6 +553,30 @@ def run_reference(args):
     log(f"reference fixture written in {time.time() - t0:.1f}s")
     global _REF_BASE_ENV
     _REF_BASE_ENV = ref_harness.make_reference_env(fixture)
+    # SURVEY 8(d) (i) one reference env, (ii) a serial loop over 8 reference envs in this process
+    import copy
+
+    arng = np.random.default_rng(7)
+    one = copy.copy(_REF_BASE_ENV)
+    loc1 = "06037" if "06037" in fips else fips[0]
+    one.reset(location=loc1, seed=1234)
+    t1 = time.perf_counter()
+    n1 = 0
+    for _ in range(min(100, max(10, K))):
+        _, _, d1, _, _ = one.step(int(arng.integers(2)))
+        n1 += 1
+        if d1:
+            one.reset(location=loc1, seed=1234)
+    single_ms = (time.perf_counter() - t1) / n1 * 1e3
+    eight = [copy.copy(_REF_BASE_ENV) for _ in range(8)]
+    for j, e8 in enumerate(eight):
+        e8.reset(location=fips[j % len(fips)], seed=100 + j)
+    t8 = time.perf_counter()
+    for _ in range(20):
+        for e8 in eight:
+            e8.step(int(arng.integers(2)))
+    sync8 = 8 * 20 / (time.perf_counter() - t8)
+    del one, eight
     n_workers = max(1, min(cores, args.ref_workers or cores))
     envs_per_worker = 2
     ctx = mp.get_context("fork")
@@ -587,6 +611,7 @@ def run_reference(args):
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": args.workload, "desc": wl["desc"], "envs_total": n_workers * envs_per_worker},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_workers, "kind": "reference", "sample": sample},
+           "reference_single_env_ms_per_step": single_ms, "reference_sync_loop_8_envs_steps_per_s": sync8,
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 
