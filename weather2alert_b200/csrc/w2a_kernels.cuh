@@ -219,10 +219,14 @@ __device__ __forceinline__ LaneSlots lane_slots(int q) {
 #define W2A_COOP_MINBLOCKS 2  // CTAs per SM the register allocation is sized for (B200 sweep: profiles/r01)
 #endif
 #ifndef W2A_COOP_AHEAD
-#define W2A_COOP_AHEAD 4  // rounds of table loads in flight ahead of the one being consumed
+#define W2A_COOP_AHEAD 3  // rounds of table loads in flight ahead of the one being consumed
+#endif
+#ifndef W2A_COOP_PRE
+#define W2A_COOP_PRE 2  // rounds of the NEXT group whose loads are issued before this group's phase C
 #endif
 constexpr int kCoopWarps = W2A_COOP_WARPS;
 constexpr int kAhead = W2A_COOP_AHEAD;
+constexpr int kPre = W2A_COOP_PRE < W2A_COOP_AHEAD ? W2A_COOP_PRE : W2A_COOP_AHEAD;
 
 // per-warp shared memory of the COOP kernel
 struct __align__(128) WarpScratch {
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
       if (e < p.n) st_stream(p.st_mut + e, mv);
       cur_cv = sv.y;
 #pragma unroll
-      for (int d = 0; d < kAhead; ++d) {
+      for (int d = 0; d < kPre; ++d) {
         const unsigned rowd = __shfl_sync(kFull, cur_tr.row, 2 * d + row_g);
         const unsigned cvd = __shfl_sync(kFull, cur_cv, 2 * d + row_g);
         ring[d] = issue_round(x_lane, w_lane, rowd, cvd, keep);
@@ -400,7 +404,14 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
     }
 
     // ---- phase B ---------------------------------------------------------------------------
-    // kAhead rounds of loads are in flight while a round is being consumed
+    // kAhead rounds of loads are in flight while a round is being consumed; the first kPre of
+    // them were issued one group earlier (open_group), the others follow now
+#pragma unroll
+    for (int d = kPre; d < kAhead; ++d) {
+      const unsigned rowd = __shfl_sync(kFull, tr.row, 2 * d + row_g);
+      const unsigned cvd = __shfl_sync(kFull, cv, 2 * d + row_g);
+      ring[d] = issue_round(x_lane, w_lane, rowd, cvd, keep);
+    }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       if (it + kAhead < 8) {
