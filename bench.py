@@ -192,7 +192,8 @@ def run_ours(args):
     s = index_streams(store, weights, n, rank, wl["augment"], args.locality)
     idx = {k: torch.from_numpy(v).to(dev) for k, v in s.items()}
     T = int(store.n_days.max())
-    variant = {"auto": _lib.STEP_AUTO, "thread": _lib.STEP_THREAD, "coop": _lib.STEP_COOP}[args.variant]
+    variant = {"auto": _lib.STEP_AUTO, "thread": _lib.STEP_THREAD, "coop": _lib.STEP_COOP,
+               "table": _lib.STEP_TABLE}[args.variant]
 
     state = core.alloc_state(n)
     obs = torch.zeros((n, 29), dtype=torch.float32, device=dev)
@@ -642,7 +643,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=list(WORKLOADS), default="cfg3_1m")
     ap.add_argument("--envs-per-gpu", type=int, default=0)
-    ap.add_argument("--variant", choices=["auto", "thread", "coop"], default="auto")
+    ap.add_argument("--variant", choices=["auto", "thread", "coop", "table"], default="auto")
     ap.add_argument("--locality", choices=["interleaved", "sorted"], default="interleaved")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from the host instead of replaying a CUDA graph per summer")
     ap.add_argument("--e2e-steps", type=int, default=30)

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 REWARD_RTOL = 1e-5   # north_star tolerance
 REWARD_ATOL = 1e-10  # rewards that underflow towards 0 (sigmoid saturated) have no relative meaning
-VARIANTS = {"thread": 1, "coop": 2}
+VARIANTS = {"thread": 1, "coop": 2, "table": 3}
 
 
 @pytest.fixture(scope="module")
@@ -294,7 +294,7 @@ def test_degenerate_table_shapes(S, Y, P, T):
     term = torch.zeros(n, dtype=torch.uint8, device="cuda")
     for i in range(min(T + 3, 40) if T < 200 else T + 2):
         act = (rng.random(n) < 0.5).astype(np.uint8)
-        core.step(state, _dev(act), obs, reward, term, variant=2 if i % 2 else 1)
+        core.step(state, _dev(act), obs, reward, term, variant=(1, 2, 3)[i % 3])
         o_ref, r_ref, d_ref, _, _ = orc.batch_step(store.feat, store.sig_code, weights.coef, st, act)
         assert_obs_equal(obs.cpu().numpy(), o_ref, f"step {i}")
         np.testing.assert_allclose(reward.cpu().numpy(), r_ref, rtol=REWARD_RTOL, atol=REWARD_ATOL)

@@ -113,6 +113,9 @@ def test_million_envs_properties(big_core):
 
     o1, r1, m1, s1 = run(1, 0, n)
     o2, r2, m2, s2 = run(2, 0, n)
+    ot, rt, mt, st_ = run(3, 0, n)  # per-step logit table variant (all envs canonical and in lock step)
+    assert torch.equal(ot.view(torch.int32), o2.view(torch.int32)) and torch.equal(mt, m2) and torch.equal(st_, s2)
+    assert torch.allclose(rt, r2, rtol=1e-6, atol=1e-9)
     assert torch.equal(o1.view(torch.int32), o2.view(torch.int32)) and torch.equal(m1, m2) and torch.equal(s1, s2)
     assert torch.allclose(r1, r2, rtol=1e-6, atol=1e-9)  # float64 sums of float32 rewards; only summation order differs
     o3, r3, m3, s3 = run(2, 0, n)

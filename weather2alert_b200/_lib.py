@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("W2A_LIB_PATH") or os.path.join(_HERE, "libw2a.so")
 
 W2A_OK = 0
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
-STEP_AUTO, STEP_THREAD, STEP_COOP = 0, 1, 2
+STEP_AUTO, STEP_THREAD, STEP_COOP, STEP_TABLE = 0, 1, 2, 3
 BUDGET_DEFAULT = -(2**31)
 OBS_DIM = 29
 
@@ -27,6 +27,7 @@ SIGNATURES = {
     "w2a_destroy": (C.c_int, [_P]),
     "w2a_set_features": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "w2a_set_coefs": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "w2a_set_county_map": (C.c_int, [_P, _P]),
     "w2a_state_bytes": (C.c_size_t, [C.c_int64]),
     "w2a_reset": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "w2a_step": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int]),

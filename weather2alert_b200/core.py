@@ -48,6 +48,10 @@ class HeatAlertCore:
         _lib.check(self._lib.w2a_set_features(ctx, _ptr(self.x), _ptr(self.n_days), _ptr(self.budget0),
                                               S, Y, T), ctx)
         _lib.check(self._lib.w2a_set_coefs(ctx, _ptr(self.w), self.P, self.Sw), ctx)
+        # feature-store county of every coefficient column: enables the per-step logit table (STEP_TABLE)
+        col_to_loc = np.array([store.fips_index.get(f, -1) for f in weights.fips_list], dtype=np.int32)
+        self.col_to_loc = torch.from_numpy(col_to_loc).to(dev)
+        _lib.check(self._lib.w2a_set_county_map(ctx, _ptr(self.col_to_loc)), ctx)
 
     def __del__(self):
         ctx = getattr(self, "ctx", None)

@@ -50,6 +50,7 @@ struct w2a_ctx {
   bool have_coefs = false;
   int64_t launches = 0;
   HostEnvs* host = nullptr;
+  void* table_scratch = nullptr;  // z_tab | xobs_t | t_cell, owned by the context (step variant TABLE)
   const void* occ_key[kMaxKernels] = {};  // occupancy (CTAs per SM) of each kernel launched so far
   int occ_val[kMaxKernels] = {};
   int n_occ = 0;
@@ -101,6 +102,18 @@ int grid_for(w2a_ctx* ctx, K kernel, int block, size_t smem, int64_t work_items_
 template <int ADT>
 int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int variant) {
   int grid = 0;
+  if (variant == W2A_STEP_TABLE) {
+    // today's logit table for every (county, posterior sample, year), then the per-env kernel
+    w2a::logit_table_kernel<<<ctx->tb.Sw, w2a::kTableThreads, 0, st>>>(ctx->tb, a.st_mut);
+    ctx->launches++;
+    constexpr int kBlock = 32 * w2a::kTableWarps;
+    int rc = grid_for(ctx, w2a::step_table_kernel<ADT>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);
+    if (rc) return rc;
+    w2a::step_table_kernel<ADT><<<grid, kBlock, w2a::kTableSmemBytes, st>>>(a);
+    ctx->launches++;
+    W2A_CUDA(ctx, cudaGetLastError());
+    return W2A_OK;
+  }
   if (variant == W2A_STEP_THREAD) {
     int rc = grid_for(ctx, w2a::step_thread_kernel<ADT>, 128, 0, 128, a.n, &grid);
     if (rc) return rc;
@@ -120,8 +133,10 @@ int step_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const void* action, in
                 const uint2* st_static, uint2* st_mut, float* obs, float* reward,
                 uint8_t* terminated, int32_t* remaining, uint8_t* at_budget, int variant) {
   if (variant == W2A_STEP_AUTO) variant = n < kCoopMinEnvs ? W2A_STEP_THREAD : W2A_STEP_COOP;
-  if (variant != W2A_STEP_THREAD && variant != W2A_STEP_COOP)
+  if (variant != W2A_STEP_THREAD && variant != W2A_STEP_COOP && variant != W2A_STEP_TABLE)
     return fail(ctx, W2A_E_INVALID, "w2a_step: unknown variant %d", variant);
+  if (variant == W2A_STEP_TABLE && !ctx->tb.z_tab)
+    return fail(ctx, W2A_E_NOTREADY, "w2a_step: W2A_STEP_TABLE needs w2a_set_county_map first");
   w2a::StepArgs a;
   a.tb = ctx->tb;
   a.st_static = st_static;
@@ -215,6 +230,10 @@ int w2a_create(int device, w2a_ctx** out) {
 int w2a_destroy(w2a_ctx* ctx) {
   if (!ctx) return W2A_OK;
   w2a_host_envs_destroy(ctx);
+  if (ctx->table_scratch) {
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->table_scratch);
+  }
   delete ctx;
   return W2A_OK;
 }
@@ -237,6 +256,8 @@ int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const
   ctx->tb.Y = Y;
   ctx->tb.T = T;
   ctx->have_features = true;
+  ctx->tb.col_to_loc = nullptr;  // a county map (and its scratch) belongs to one set of tables
+  ctx->tb.z_tab = nullptr;
   return W2A_OK;
 }
 
@@ -251,6 +272,35 @@ int w2a_set_coefs(w2a_ctx* ctx, const float* w, int P, int S_w) {
   ctx->tb.P = P;
   ctx->tb.Sw = S_w;
   ctx->have_coefs = true;
+  ctx->tb.col_to_loc = nullptr;
+  ctx->tb.z_tab = nullptr;
+  return W2A_OK;
+}
+
+int w2a_set_county_map(w2a_ctx* ctx, const int32_t* col_to_loc) {
+  if (!ctx) return W2A_E_INVALID;
+  if (!ctx->have_features || !ctx->have_coefs)
+    return fail(ctx, W2A_E_NOTREADY, "w2a_set_county_map: call w2a_set_features and w2a_set_coefs first");
+  if (!col_to_loc) return fail(ctx, W2A_E_INVALID, "w2a_set_county_map: NULL map");
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->table_scratch) {
+    W2A_CUDA(ctx, cudaFree(ctx->table_scratch));
+    ctx->table_scratch = nullptr;
+    ctx->tb.z_tab = nullptr;
+  }
+  const w2a::Tables& tb = ctx->tb;
+  const size_t z_bytes = static_cast<size_t>(tb.Sw) * tb.P * tb.Y * sizeof(double2);
+  const size_t o_bytes = static_cast<size_t>(tb.S) * tb.Y * 32 * sizeof(float);
+  W2A_CUDA(ctx, cudaMalloc(&ctx->table_scratch, z_bytes + o_bytes + 256));
+  W2A_CUDA(ctx, cudaMemset(ctx->table_scratch, 0, z_bytes + o_bytes + 256));
+  char* base = static_cast<char*>(ctx->table_scratch);
+  ctx->tb.z_tab = reinterpret_cast<double2*>(base);
+  ctx->tb.xobs_t = reinterpret_cast<float*>(base + z_bytes);
+  ctx->tb.t_cell = reinterpret_cast<int*>(base + z_bytes + o_bytes);
+  ctx->tb.col_to_loc = col_to_loc;
+  const unsigned long long one40 = 1ull << 40;
+  ctx->tb.magic_T = (one40 + tb.T - 1) / tb.T;
+  ctx->tb.magic_Y = (one40 + tb.Y - 1) / tb.Y;
   return W2A_OK;
 }
 

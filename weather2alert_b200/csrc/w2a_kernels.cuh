@@ -45,12 +45,22 @@ struct Tables {
   // remaining_budget, bias
   const float* w;
   int S, Y, T, P, Sw;
+  // ---- the per-step logit table (step variant TABLE), all null / 0 until w2a_set_county_map ----
+  const int32_t* col_to_loc;  // [Sw] feature-store county of coefficient column `col`, -1 = none
+  double2* z_tab;             // [Sw*P, Y] (z_b, z_e) table parts of day t_cell for (col, p, year)
+  float* xobs_t;              // [S*Y, 32] float32 observation rows (slot order) of day t_cell
+  int* t_cell;                // the day the two tables were built for
+  unsigned long long magic_T, magic_Y;  // ceil(2^40 / T), ceil(2^40 / Y): exact n / d for n < 2^24, d < 2^16
 };
+
+__device__ __forceinline__ unsigned div_magic(unsigned n, unsigned long long magic) {
+  return static_cast<unsigned>((static_cast<unsigned long long>(n) * magic) >> 40);
+}
 
 struct StepArgs {
   Tables tb;
   const uint2* st_static;  // x: row0 (24 bit) | n_days << 24 ; y: coefficient record index
-  uint2* st_mut;           // x: remaining budget (int32)      ; y: t | streak<<8 | win14<<16 | done<<30
+  uint2* st_mut;           // x: remaining budget (int32)      ; y: t | streak<<8 | win14<<16 | done<<30 | canonical<<31
   const void* action;
   float* obs;
   float* reward;
@@ -132,7 +142,7 @@ __device__ __forceinline__ Transition advance(uint2 sv, uint2& mv, int a) {
   const int s2 = o.done ? streak : (o.act ? streak + 1 : 0);
   mv.x = static_cast<unsigned>(rem);
   mv.y = static_cast<unsigned>(t2) | (static_cast<unsigned>(s2) << 8) | (win << 16) |
-         (static_cast<unsigned>(o.done) << 30);
+         (static_cast<unsigned>(o.done) << 30) | (pk & 0x80000000u);  // bit 31: canonical (county, column) pair
   return o;
 }
 
@@ -495,6 +505,208 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
 }
 
 // =========================================================================================
+// step, variant TABLE: two launches per step for big, non-augmented env sets.
+//
+// The table part of both logits depends on (county, year, day, posterior sample) only.  With
+// more envs than such combinations (S*Y*P = 820 600 for the real shapes) it is cheaper to
+// evaluate ALL combinations of today once -- one CTA per county keeps that county's P
+// coefficient records in registers and its Y day-rows in shared memory, perfect locality, no
+// per-env gather of 512 bytes -- and to let every env pick its 16-byte entry:
+//   logit_table_kernel   z_tab[(col*P + p)*Y + y] = (z_b, z_e) table parts (gate included) and
+//                        xobs_t[s*Y + y][29] = the float32 observation row, for day t_cell
+//   step_table_kernel    per env: transition, z = z_tab entry + agent terms, sigmoids, reward;
+//                        per warp: the 32 observation rows are copies of xobs_t rows, patched
+//                        with the agent slots, and leave through one bulk (TMA) store.
+// The day is taken from env 0; an env on another day, or whose coefficient column is not its
+// own county (augmentation, quirk Q6), computes its logits and row directly from the tables
+// (same arithmetic as the THREAD kernel), so the result never depends on the envs being in
+// lock step -- only the speed does.
+// =========================================================================================
+constexpr int kTableThreads = 128;
+__global__ void __launch_bounds__(kTableThreads) logit_table_kernel(const Tables tb, const uint2* st_mut) {
+  // [year][13 x double2]: positions (0,1) .. (22,23) and (significance code, gate)
+  __shared__ double2 xs[32][13];
+  const int col = blockIdx.x;
+  const int s = __ldg(tb.col_to_loc + col);
+  const int t = min(static_cast<int>(__ldg(&st_mut[0].y) & 0xffu), tb.T - 1);
+  if (col == 0 && threadIdx.x == 0) *tb.t_cell = t;
+  if (s < 0) return;
+  for (int y0 = 0; y0 < tb.Y; y0 += 32) {
+    const int ny = min(32, tb.Y - y0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ny * 13; i += kTableThreads) {
+      const int y = i / 13, k = i - y * 13;
+      xs[y][k] = __ldg(reinterpret_cast<const double2*>(
+                           tb.x + (static_cast<size_t>(s * tb.Y + y0 + y) * tb.T + t) * kXStride) + k);
+    }
+    __syncthreads();
+    // observation rows of the county's years, slot order, float32
+    for (int i = threadIdx.x; i < ny * 32; i += kTableThreads) {
+      const int y = i >> 5, slot = i & 31;
+      const double* xr = reinterpret_cast<const double*>(xs[y]);
+      float v = 0.f;
+      if (slot < 23) v = static_cast<float>(xr[slot]);
+      else if (slot == 26) v = static_cast<float>(xr[23]);
+      else if (slot == 27) v = sig_to_obs(static_cast<float>(xr[kXSig]));
+      tb.xobs_t[static_cast<size_t>(s * tb.Y + y0 + y) * 32 + slot] = v;
+    }
+    // logits: one thread per posterior sample keeps both heads' 25 coefficients in registers and walks
+    // the years; the day-rows are broadcast 128-bit shared-memory reads
+    for (int pp = threadIdx.x; pp < tb.P; pp += kTableThreads) {
+      const float4* wr = reinterpret_cast<const float4*>(tb.w + static_cast<size_t>(col * tb.P + pp) * kWStride);
+      double wb[26], we[26];
+#pragma unroll
+      for (int k = 0; k < 13; ++k) {  // floats 4k..4k+3 = (b,e) of positions 2k, 2k+1 (24: zeros, 25: gate (0,1))
+        const float4 v = __ldg(wr + k);
+        wb[2 * k] = v.x; we[2 * k] = v.y; wb[2 * k + 1] = v.z; we[2 * k + 1] = v.w;
+      }
+      double2* zout = tb.z_tab + static_cast<size_t>(col * tb.P + pp) * tb.Y + y0;
+      for (int y = 0; y < ny; ++y) {
+        double zb = 0.0, ze = 0.0;
+#pragma unroll
+        for (int k = 0; k < 13; ++k) {
+          const double2 xv = xs[y][k];
+          if (k < 12) {
+            zb = fma(xv.x, wb[2 * k], zb); ze = fma(xv.x, we[2 * k], ze);
+            zb = fma(xv.y, wb[2 * k + 1], zb); ze = fma(xv.y, we[2 * k + 1], ze);
+          } else {  // (significance code, gate): only the gate enters, with its (0, 1) coefficients
+            zb = fma(xv.y, wb[25], zb); ze = fma(xv.y, we[25], ze);
+          }
+        }
+        zout[y] = make_double2(zb, ze);
+      }
+    }
+  }
+}
+
+struct __align__(128) TableScratchWarp {
+  float obs[32 * kObsDim];
+};
+constexpr int kTableWarps = 8;
+constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScratchWarp));
+
+template <int ADT>
+__global__ void __launch_bounds__(32 * kTableWarps, 4) step_table_kernel(const StepArgs p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* const stage = reinterpret_cast<TableScratchWarp*>(smem_raw)[threadIdx.x >> 5].obs;
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 7;
+  const int g = lane >> 3;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int n_groups = (p.n + 31) >> 5;
+  const int t_table = *p.tb.t_cell;
+  const unsigned long long keep = l2_policy_evict_last();
+  const unsigned long long stream_out = l2_policy_evict_first();
+  const bool obs_aligned = (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
+  const float4* const xobs_lane = reinterpret_cast<const float4*>(p.tb.xobs_t) + q;
+  float* const my_row = stage + lane * kObsDim;
+  bool bulk_pending = false;
+
+  for (int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wg < n_groups; wg += warps_total) {
+    const int base = wg << 5;
+    const int e = base + lane;
+    const bool valid = e < p.n;
+    const int ec = valid ? e : p.n - 1;
+    const uint2 sv = ld_stream(p.st_static + ec);
+    uint2 mv = ld_stream(p.st_mut + ec);
+    const int a = load_action<ADT>(p.action, ec);
+    const int t_before = mv.y & 0xff;
+    const bool canon = (mv.y >> 31) != 0;
+    const Transition tr = advance(sv, mv, a);
+    if (valid) st_stream(p.st_mut + e, mv);
+    const unsigned cv = sv.y;
+    const unsigned sy = div_magic(sv.x & 0xffffffu, p.tb.magic_T);
+    const unsigned yr = sy - div_magic(sy, p.tb.magic_Y) * static_cast<unsigned>(p.tb.Y);
+    const bool fast = canon && t_before == t_table;
+    const bool write_obs = valid && !tr.done;
+    const unsigned wmask = __ballot_sync(kFull, write_obs);
+    if (bulk_pending) {  // the previous group's bulk store must have finished reading the staging buffer
+      if (lane == 0) bulk_store_wait_read();
+      __syncwarp();
+      bulk_pending = false;
+    }
+    // ---- logits -------------------------------------------------------------------------------
+    const float4* wo = reinterpret_cast<const float4*>(p.tb.w + static_cast<size_t>(cv) * kWStride + kWOther);
+    const float4 o0 = ldg_keep(wo, keep), o1 = ldg_keep(wo + 1, keep);
+    double zb, ze;
+    if (fast) {
+      const double2 z = __ldg(p.tb.z_tab + static_cast<size_t>(cv) * p.tb.Y + yr);
+      zb = z.x;
+      ze = z.y;
+    } else {  // off-day or non-canonical env: straight from the tables, row staged by its own thread
+      const double* xr = p.tb.x + static_cast<size_t>(tr.row) * kXStride;
+      const float* wv = p.tb.w + static_cast<size_t>(cv) * kWStride;
+      zb = __ldg(xr + 25) * static_cast<double>(__ldg(wv + 50));
+      ze = __ldg(xr + 25) * static_cast<double>(__ldg(wv + 51));
+      for (int u = 0; u < 24; ++u) {
+        const double x = __ldg(xr + u);
+        zb = fma(x, static_cast<double>(__ldg(wv + 2 * u)), zb);
+        ze = fma(x, static_cast<double>(__ldg(wv + 2 * u + 1)), ze);
+        my_row[slot_of_feature(u)] = static_cast<float>(x);
+      }
+      my_row[27] = sig_to_obs(static_cast<float>(__ldg(xr + kXSig)));
+    }
+    {
+      const double f_lag = static_cast<double>(tr.lag), f_streak = static_cast<double>(tr.streak),
+                   f_rem = static_cast<double>(tr.rem);
+      zb += static_cast<double>(o1.z);
+      ze += static_cast<double>(o1.w);
+      zb = fma(f_lag, static_cast<double>(o0.x), zb);
+      ze = fma(f_lag, static_cast<double>(o0.y), ze);
+      zb = fma(f_streak, static_cast<double>(o0.z), zb);
+      ze = fma(f_streak, static_cast<double>(o0.w), ze);
+      zb = fma(f_rem, static_cast<double>(o1.x), zb);
+      ze = fma(f_rem, static_cast<double>(o1.y), ze);
+    }
+    if (valid) {
+      const double baseline = expit(zb);
+      const double eff = tr.act ? expit(ze) : 0.0;
+      __stcs(p.reward + e, static_cast<float>(kRewardScale * baseline * (1.0 - eff)));
+      p.terminated[e] = static_cast<uint8_t>(tr.done);
+      if (p.remaining) __stcs(p.remaining + e, tr.rem);
+      if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
+    }
+    __syncwarp();
+    // ---- observation rows: 8 lanes copy one float32 row, four neighbouring envs per round -----------
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int j = 4 * it + g;
+      const unsigned syj = __shfl_sync(kFull, sy, j);
+      const int fastj = __shfl_sync(kFull, static_cast<int>(fast), j);
+      if (fastj) {
+        const float4 v = __ldg(xobs_lane + static_cast<size_t>(syj) * 8);
+        float* st = stage + j * kObsDim + 4 * q;
+        st[0] = v.x;
+        if (q < 7) {
+          st[1] = v.y;
+          st[2] = v.z;
+          st[3] = v.w;
+        }
+      }
+    }
+    __syncwarp();
+    my_row[23] = static_cast<float>(tr.lag);
+    my_row[24] = static_cast<float>(tr.streak);
+    my_row[25] = static_cast<float>(tr.rem);
+    my_row[28] = static_cast<float>(tr.cnt14);
+    fence_proxy_async_smem();
+    __syncwarp();
+    float* const ob = p.obs + static_cast<size_t>(base) * kObsDim;
+    if (wmask == kFull && obs_aligned) {
+      if (lane == 0) bulk_store(ob, stage, kObsBlockBytes, stream_out);
+      bulk_pending = true;
+    } else if (wmask != 0u) {
+      for (int i = lane; i < 32 * kObsDim; i += 32) {
+        const int env = (i * 565) >> 14;  // i / 29 for i < 928
+        if ((wmask >> env) & 1u) st_stream(ob + i, stage[i]);
+      }
+    }
+    __syncwarp();
+  }
+  if (bulk_pending && lane == 0) bulk_store_wait_read();
+}
+
+// =========================================================================================
 // reset: host index streams -> state + first observation (env.py:155-184).
 // Same warp shape and lane roles as the COOP step; observations go straight to global
 // memory (a reset happens once per 153 steps).
@@ -520,9 +732,13 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
     if (budget == INT32_MIN) budget = __ldg(p.tb.budget0 + sy);  // env.py:167-170
     const unsigned cv = static_cast<unsigned>(__ldcs(p.coef_col + ec)) * static_cast<unsigned>(p.tb.P) +
                         static_cast<unsigned>(__ldcs(p.coef_idx + ec));
+    // canonical pair: the coefficient column is the episode's own county (no similar-county
+    // substitution, Q6), so the per-step logit table applies to this env
+    const int colv = __ldcs(p.coef_col + ec);
+    const bool canon = p.tb.col_to_loc != nullptr && __ldg(p.tb.col_to_loc + colv) == __ldcs(p.loc + ec);
     if (take) {
       st_stream(p.st_static + e, make_uint2(row0 | (nd << 24), cv));
-      st_stream(p.st_mut + e, make_uint2(static_cast<unsigned>(budget), 0u));  // t = streak = win = 0
+      st_stream(p.st_mut + e, make_uint2(static_cast<unsigned>(budget), canon ? 0x80000000u : 0u));  // t = streak = win = 0
       if (p.remaining) p.remaining[e] = budget;
     }
 #pragma unroll
@@ -762,7 +978,7 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
       p.ep_return[e] = total;
       p.st_mut[e] = make_uint2(static_cast<unsigned>(rem),
                                static_cast<unsigned>(t) | (static_cast<unsigned>(streak) << 8) | (win << 16) |
-                                   ((done ? 1u : 0u) << 30));
+                                   ((done ? 1u : 0u) << 30) | (mv.y & 0x80000000u));
       if (done) {
         acc[kStEpisodes] += 1.0;
         acc[kStReturnSum] += total;
