@@ -174,6 +174,6 @@ def test_rollout_at_baseline_size_matches_stepping():
         core.step(st_s, acts[k], obs, reward, term)
         total += reward.double()
     assert bool(term.all()) and torch.equal(st_r, st_s)
-    assert torch.allclose(ret, total, rtol=1e-6, atol=0)  # float32 rounding of each stepped reward
+    assert torch.allclose(ret, total, rtol=2e-6, atol=0)  # float32 rounding and the float32 sigmoid (<= 3e-7) of each stepped reward
     assert float(stats[0]) == n and float(stats[3]) == 153 * n
     assert float(stats[1]) == pytest.approx(float(ret.sum()), rel=1e-9)

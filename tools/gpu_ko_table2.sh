@@ -1,0 +1,5 @@
+# usage: gpu_ko_table2.sh ko...   warm per-kernel times of the TABLE variant with parts knocked out
+for c in $@; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -DW2A_TABLE_KO=$c -I include -o /tmp/lib_ko$c.so weather2alert_b200/csrc/w2a.cu 2>/dev/null
+  echo "KO=$c"; W2A_LIB_PATH=/tmp/lib_ko$c.so bash tools/gpu_warm_launches.sh --variant table | tail -2
+done

@@ -282,6 +282,9 @@ int w2a_set_county_map(w2a_ctx* ctx, const int32_t* col_to_loc) {
   if (!ctx->have_features || !ctx->have_coefs)
     return fail(ctx, W2A_E_NOTREADY, "w2a_set_county_map: call w2a_set_features and w2a_set_coefs first");
   if (!col_to_loc) return fail(ctx, W2A_E_INVALID, "w2a_set_county_map: NULL map");
+  if (static_cast<int64_t>(ctx->tb.Sw) * ctx->tb.P >= (int64_t{1} << 24) || ctx->tb.P >= (1 << 16) ||
+      ctx->tb.T >= (1 << 16) || ctx->tb.Y >= (1 << 14))
+    return fail(ctx, W2A_E_INVALID, "w2a_set_county_map: tables too large for the per-step logit table");
   W2A_CUDA(ctx, cudaSetDevice(ctx->device));
   if (ctx->table_scratch) {
     W2A_CUDA(ctx, cudaFree(ctx->table_scratch));
@@ -289,12 +292,14 @@ int w2a_set_county_map(w2a_ctx* ctx, const int32_t* col_to_loc) {
     ctx->tb.z_tab = nullptr;
   }
   const w2a::Tables& tb = ctx->tb;
-  const size_t z_bytes = static_cast<size_t>(tb.Sw) * tb.P * tb.Y * sizeof(double2);
+  const int z_lines = (tb.Y + w2a::kZPerLine - 1) / w2a::kZPerLine;
+  const size_t z_bytes = static_cast<size_t>(tb.Sw) * tb.P * z_lines * 128;
   const size_t o_bytes = static_cast<size_t>(tb.S) * tb.Y * 32 * sizeof(float);
   W2A_CUDA(ctx, cudaMalloc(&ctx->table_scratch, z_bytes + o_bytes + 256));
   W2A_CUDA(ctx, cudaMemset(ctx->table_scratch, 0, z_bytes + o_bytes + 256));
   char* base = static_cast<char*>(ctx->table_scratch);
-  ctx->tb.z_tab = reinterpret_cast<double2*>(base);
+  ctx->tb.z_tab = reinterpret_cast<float4*>(base);
+  ctx->tb.z_lines = z_lines;
   ctx->tb.xobs_t = reinterpret_cast<float*>(base + z_bytes);
   ctx->tb.t_cell = reinterpret_cast<int*>(base + z_bytes + o_bytes);
   ctx->tb.col_to_loc = col_to_loc;

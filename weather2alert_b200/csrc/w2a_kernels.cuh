@@ -47,10 +47,15 @@ struct Tables {
   int S, Y, T, P, Sw;
   // ---- the per-step logit table (step variant TABLE), all null / 0 until w2a_set_county_map ----
   const int32_t* col_to_loc;  // [Sw] feature-store county of coefficient column `col`, -1 = none
-  double2* z_tab;             // [Sw*P, Y] (z_b, z_e) table parts of day t_cell for (col, p, year)
+  // per (col, p): z_lines lines of 128 bytes; each line = the 6 agent coefficients (lag, streak,
+  // remaining budget as (b, e) pairs; 24 bytes + 8 zero) followed by the (z_b, z_e) float64 table
+  // parts (gate and bias included) of 6 consecutive years for day t_cell: an env finds all it
+  // needs for its logits in ONE cache line
+  float4* z_tab;
+  int z_lines;                // ceil(Y / 6)
   float* xobs_t;              // [S*Y, 32] float32 observation rows (slot order) of day t_cell
   int* t_cell;                // the day the two tables were built for
-  unsigned long long magic_T, magic_Y;  // ceil(2^40 / T), ceil(2^40 / Y): exact n / d for n < 2^24, d < 2^16
+  unsigned long long magic_T, magic_Y;  // ceil(2^40 / d): exact n / d for n < 2^24, d < 2^16
 };
 
 __device__ __forceinline__ unsigned div_magic(unsigned n, unsigned long long magic) {
@@ -97,8 +102,38 @@ __device__ __forceinline__ int load_action(const void* a, int e) {
   return __ldcs(reinterpret_cast<const long long*>(a) + e) != 0;
 }
 
-// scipy.special.expit in float64, as used at env.py:211,218
+// scipy.special.expit in float64, as used at env.py:211,218 (the episode-fused rollout sums float64 returns)
 __device__ __forceinline__ double expit(double z) { return 1.0 / (1.0 + exp(-z)); }
+
+// The step kernels hand the reward back as float32, so they evaluate the sigmoids in float32 too --
+// but on an argument reduced in float64: t = -z*log2(e) = n + f exactly (|f| <= 1/2), 2^f by
+// MUFU.EX2, 2^n by exponent arithmetic, the reciprocal by MUFU.RCP.  Relative error <= 3e-7 for any
+// z (the reference tolerance is 1e-5); ~14 instructions instead of ~60 for the float64 exp + divide.
+__device__ __forceinline__ float sigmoid_f32(double z) {
+  double t = z * -1.4426950408889634;          // 2^t = exp(-z)
+  t = fmin(fmax(t, -126.0), 126.0);            // keeps 2^t a finite float32; sigmoid is 1 / 1e-38 out there
+  const double magic = 6755399441055744.0;     // 1.5 * 2^52: t + magic holds rint(t) in its low word
+  const double tn = t + magic;
+  const int n = __double2loint(tn);
+  const float f = static_cast<float>(t - (tn - magic));
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(f));
+  const float p = e * __int_as_float((n + 127) << 23);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + p));
+  return r;
+}
+// reward = -1000/152 * sigmoid(z_b) * (1 - sigmoid(z_e) * [heat_qi > 0.5] * action)  (env.py:211-221).
+// 1 - sigmoid(z_e) is taken as sigmoid(-z_e), which has no cancellation; the reference's float64
+// `1 - expit(z_e)` does cancel, visibly (beyond 1e-5 relative) once z_e > ~25, so from z_e > 20 on the
+// reference's own float64 expression is evaluated instead (a branch real coefficients never take) and
+// the result follows the reference's rounding there as well.  The gate column makes z_e = -1e300 when
+// heat_qi <= 0.5, and sigmoid(1e300) is exactly 1.
+__device__ __forceinline__ float step_reward(double zb, double ze, int act) {
+  const float b = sigmoid_f32(zb);
+  float q = 1.0f;
+  if (act) q = ze > 20.0 ? static_cast<float>(1.0 - expit(ze)) : sigmoid_f32(-ze);
+  return static_cast<float>(kRewardScale) * b * q;
+}
 
 // observation slot of table feature u (u = 0..23): slots 0..22, then 26 (issued_in_advance)
 __host__ __device__ __forceinline__ int slot_of_feature(int u) { return u < 23 ? u : 26; }
@@ -182,9 +217,7 @@ __global__ void __launch_bounds__(128) step_thread_kernel(const StepArgs p) {
       ze = fma(other[k], static_cast<double>(__ldg(wv + kWOther + 2 * k + 1)), ze);
     }
     // reward = -1000/152 * sigmoid(z_b) * (1 - sigmoid(z_e) * [heat_qi > 0.5] * action)  (env.py:211-221)
-    const double baseline = expit(zb);
-    const double eff = (tr.act && heat_qi > 0.5) ? expit(ze) : 0.0;
-    p.reward[e] = static_cast<float>(kRewardScale * baseline * (1.0 - eff));
+    p.reward[e] = step_reward(zb, ze, tr.act && heat_qi > 0.5);
     p.terminated[e] = static_cast<uint8_t>(tr.done);
     if (p.remaining) p.remaining[e] = tr.rem;
     if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
@@ -477,10 +510,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
       my_row[27] = sig_to_obs(my_row[27]);
       my_row[28] = static_cast<float>(tr.cnt14);
       if (valid) {
-        // reward = -1000/152 * sigmoid(z_b) * (1 - sigmoid(z_e) * [heat_qi > 0.5] * action)  (env.py:211-221)
-        const double baseline = expit(zb);
-        const double eff = tr.act ? expit(ze) : 0.0;
-        __stcs(p.reward + e, static_cast<float>(kRewardScale * baseline * (1.0 - eff)));
+        __stcs(p.reward + e, step_reward(zb, ze, tr.act));
         p.terminated[e] = static_cast<uint8_t>(tr.done);
         if (p.remaining) __stcs(p.remaining + e, tr.rem);
         if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
@@ -511,70 +541,124 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
 // more envs than such combinations (S*Y*P = 820 600 for the real shapes) it is cheaper to
 // evaluate ALL combinations of today once -- one CTA per county keeps that county's P
 // coefficient records in registers and its Y day-rows in shared memory, perfect locality, no
-// per-env gather of 512 bytes -- and to let every env pick its 16-byte entry:
-//   logit_table_kernel   z_tab[(col*P + p)*Y + y] = (z_b, z_e) table parts (gate included) and
-//                        xobs_t[s*Y + y][29] = the float32 observation row, for day t_cell
-//   step_table_kernel    per env: transition, z = z_tab entry + agent terms, sigmoids, reward;
-//                        per warp: the 32 observation rows are copies of xobs_t rows, patched
-//                        with the agent slots, and leave through one bulk (TMA) store.
+// per-env gather of 512 bytes -- and to let every env pick its entry:
+//   logit_table_kernel   z_tab line (col*P + p, year / 6) = agent coefficients + (z_b, z_e) of six
+//                        years (gate and bias included), and xobs_t[s*Y + y][29] = the float32
+//                        observation row, for day t_cell
+//   step_table_kernel    per env: transition, z = its entry + agent terms, sigmoids, reward (one
+//                        gathered line); per warp: the 32 observation rows are copies of xobs_t
+//                        rows (one more gathered line per env), patched with the agent slots, and
+//                        leave through one bulk (TMA) store.
 // The day is taken from env 0; an env on another day, or whose coefficient column is not its
 // own county (augmentation, quirk Q6), computes its logits and row directly from the tables
 // (same arithmetic as the THREAD kernel), so the result never depends on the envs being in
 // lock step -- only the speed does.
 // =========================================================================================
+#ifndef W2A_TABLE_KO  // experiments only (tools/gpu_ko_table.sh): knock parts of the kernel out, results become wrong
+#define W2A_TABLE_KO 0
+#endif
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 constexpr int kTableThreads = 128;
-__global__ void __launch_bounds__(kTableThreads) logit_table_kernel(const Tables tb, const uint2* st_mut) {
-  // [year][13 x double2]: positions (0,1) .. (22,23) and (significance code, gate)
-  __shared__ double2 xs[32][13];
+constexpr int kTableYears = 18;     // years per shared-memory pass (a multiple of kZPerLine)
+constexpr int kZPerLine = 6;        // (z_b, z_e) entries per 128-byte line, after the 32-byte head
+constexpr int kWsStride = 17;       // float4 per staged coefficient record: banks 4*p, conflict-free
+__global__ void __launch_bounds__(kTableThreads, 3) logit_table_kernel(const Tables tb, const uint2* st_mut) {
+  // day-rows [year][13 x double2]: positions (0,1) .. (22,23) and (significance code, gate)
+  __shared__ double2 xs[kTableYears][13];
+  __shared__ float4 ws[kTableThreads * kWsStride];
+  const int tid = threadIdx.x;
   const int col = blockIdx.x;
   const int s = __ldg(tb.col_to_loc + col);
   const int t = min(static_cast<int>(__ldg(&st_mut[0].y) & 0xffu), tb.T - 1);
-  if (col == 0 && threadIdx.x == 0) *tb.t_cell = t;
+  if (col == 0 && tid == 0) *tb.t_cell = t;
   if (s < 0) return;
-  for (int y0 = 0; y0 < tb.Y; y0 += 32) {
-    const int ny = min(32, tb.Y - y0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < ny * 13; i += kTableThreads) {
-      const int y = i / 13, k = i - y * 13;
-      xs[y][k] = __ldg(reinterpret_cast<const double2*>(
-                           tb.x + (static_cast<size_t>(s * tb.Y + y0 + y) * tb.T + t) * kXStride) + k);
+  for (int p0 = 0; p0 < tb.P; p0 += kTableThreads) {
+    const int np = min(kTableThreads, tb.P - p0);
+    // the county's coefficient records and (per pass) day-rows go global -> shared memory as
+    // asynchronous 16-byte copies: all in flight at once, no staging registers
+    __syncthreads();  // earlier readers of ws are done
+    {
+      const float4* wsrc = reinterpret_cast<const float4*>(tb.w + static_cast<size_t>(col * tb.P + p0) * kWStride);
+      for (int i = tid; i < np * 16; i += kTableThreads) cp_async16(&ws[(i >> 4) * kWsStride + (i & 15)], wsrc + i);
     }
-    __syncthreads();
-    // observation rows of the county's years, slot order, float32
-    for (int i = threadIdx.x; i < ny * 32; i += kTableThreads) {
-      const int y = i >> 5, slot = i & 31;
-      const double* xr = reinterpret_cast<const double*>(xs[y]);
-      float v = 0.f;
-      if (slot < 23) v = static_cast<float>(xr[slot]);
-      else if (slot == 26) v = static_cast<float>(xr[23]);
-      else if (slot == 27) v = sig_to_obs(static_cast<float>(xr[kXSig]));
-      tb.xobs_t[static_cast<size_t>(s * tb.Y + y0 + y) * 32 + slot] = v;
-    }
-    // logits: one thread per posterior sample keeps both heads' 25 coefficients in registers and walks
-    // the years; the day-rows are broadcast 128-bit shared-memory reads
-    for (int pp = threadIdx.x; pp < tb.P; pp += kTableThreads) {
-      const float4* wr = reinterpret_cast<const float4*>(tb.w + static_cast<size_t>(col * tb.P + pp) * kWStride);
-      double wb[26], we[26];
-#pragma unroll
-      for (int k = 0; k < 13; ++k) {  // floats 4k..4k+3 = (b,e) of positions 2k, 2k+1 (24: zeros, 25: gate (0,1))
-        const float4 v = __ldg(wr + k);
-        wb[2 * k] = v.x; we[2 * k] = v.y; wb[2 * k + 1] = v.z; we[2 * k + 1] = v.w;
+    bool w_staged = false;
+    double wb[26], we[26];
+    float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 head2 = make_float2(0.f, 0.f);
+    double bias_b = 0.0, bias_e = 0.0;
+    for (int y0 = 0; y0 < tb.Y; y0 += kTableYears) {
+      const int ny = min(kTableYears, tb.Y - y0);
+      if (y0 > 0) __syncthreads();  // earlier readers of xs are done
+      for (int i = tid; i < ny * 13; i += kTableThreads) {
+        const int y = i / 13, k = i - y * 13;
+        cp_async16(&xs[y][k], reinterpret_cast<const double2*>(
+                                  tb.x + (static_cast<size_t>(s * tb.Y + y0 + y) * tb.T + t) * kXStride) + k);
       }
-      double2* zout = tb.z_tab + static_cast<size_t>(col * tb.P + pp) * tb.Y + y0;
-      for (int y = 0; y < ny; ++y) {
-        double zb = 0.0, ze = 0.0;
-#pragma unroll
-        for (int k = 0; k < 13; ++k) {
-          const double2 xv = xs[y][k];
-          if (k < 12) {
-            zb = fma(xv.x, wb[2 * k], zb); ze = fma(xv.x, we[2 * k], ze);
-            zb = fma(xv.y, wb[2 * k + 1], zb); ze = fma(xv.y, we[2 * k + 1], ze);
-          } else {  // (significance code, gate): only the gate enters, with its (0, 1) coefficients
-            zb = fma(xv.y, wb[25], zb); ze = fma(xv.y, we[25], ze);
-          }
+      cp_async_wait_all();
+      __syncthreads();
+      if (p0 == 0) {  // observation rows of the county's years, slot order, float32
+        for (int i = tid; i < ny * 32; i += kTableThreads) {
+          const int y = i >> 5, slot = i & 31;
+          const double* xr = reinterpret_cast<const double*>(xs[y]);
+          float v = 0.f;
+          if (slot < 23) v = static_cast<float>(xr[slot]);
+          else if (slot == 26) v = static_cast<float>(xr[23]);
+          else if (slot == 27) v = sig_to_obs(static_cast<float>(xr[kXSig]));
+          tb.xobs_t[static_cast<size_t>(s * tb.Y + y0 + y) * 32 + slot] = v;
         }
-        zout[y] = make_double2(zb, ze);
       }
+      if (tid < np) {
+        if (!w_staged) {  // this thread's sample: both heads' coefficients to float64 registers
+#pragma unroll
+          for (int k = 0; k < 13; ++k) {  // floats 4k..4k+3 = (b,e) of positions 2k, 2k+1 (24: zeros, 25: gate (0,1))
+            const float4 v = ws[tid * kWsStride + k];
+            wb[2 * k] = v.x; we[2 * k] = v.y; wb[2 * k + 1] = v.z; we[2 * k + 1] = v.w;
+          }
+          head = ws[tid * kWsStride + 14];  // lag (b,e), streak (b,e)
+          const float4 tail = ws[tid * kWsStride + 15];  // remaining budget (b,e), bias (b,e)
+          head2 = make_float2(tail.x, tail.y);
+          bias_b = tail.z;
+          bias_e = tail.w;
+        }
+        // logits, two years at a time (four independent accumulation chains); the day-rows are
+        // broadcast 128-bit shared-memory reads
+        float4* rec = tb.z_tab + static_cast<size_t>(col * tb.P + p0 + tid) * (tb.z_lines * 8);
+        for (int y = 0; y < ((W2A_TABLE_KO & 64) ? 1 : ny); y += 2) {
+          const int y1 = min(y + 1, ny - 1);
+          double zb0 = 0.0, ze0 = 0.0, zb1 = 0.0, ze1 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 13; ++k) {
+            const double2 xa = xs[y][k], xb = xs[y1][k];
+            if (k < 12) {
+              zb0 = fma(xa.x, wb[2 * k], zb0); ze0 = fma(xa.x, we[2 * k], ze0);
+              zb1 = fma(xb.x, wb[2 * k], zb1); ze1 = fma(xb.x, we[2 * k], ze1);
+              zb0 = fma(xa.y, wb[2 * k + 1], zb0); ze0 = fma(xa.y, we[2 * k + 1], ze0);
+              zb1 = fma(xb.y, wb[2 * k + 1], zb1); ze1 = fma(xb.y, we[2 * k + 1], ze1);
+            } else {  // (significance code, gate): only the gate enters, with its (0, 1) coefficients
+              zb0 = fma(xa.y, wb[25], zb0); ze0 = fma(xa.y, we[25], ze0);
+              zb1 = fma(xb.y, wb[25], zb1); ze1 = fma(xb.y, we[25], ze1);
+            }
+          }
+          const int ya = y0 + y, yb = y0 + y1;
+          double2* za = reinterpret_cast<double2*>(rec + (ya / kZPerLine) * 8 + 2) + ya % kZPerLine;
+          double2* zb = reinterpret_cast<double2*>(rec + (yb / kZPerLine) * 8 + 2) + yb % kZPerLine;
+          if ((W2A_TABLE_KO & 128) && zb0 != 12345.0) continue;
+          *za = make_double2(zb0 + bias_b, ze0 + bias_e);
+          if (y1 != y) *zb = make_double2(zb1 + bias_b, ze1 + bias_e);
+        }
+        // line heads of the lines this pass touched (kTableYears is a multiple of kZPerLine)
+        for (int l = y0 / kZPerLine; l * kZPerLine < y0 + ny; ++l) {
+          rec[l * 8] = head;
+          rec[l * 8 + 1] = make_float4(head2.x, head2.y, 0.f, 0.f);
+        }
+      }
+      w_staged = true;
     }
   }
 }
@@ -585,8 +669,12 @@ struct __align__(128) TableScratchWarp {
 constexpr int kTableWarps = 8;
 constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScratchWarp));
 
+#ifndef W2A_TABLE_MINBLOCKS
+#define W2A_TABLE_MINBLOCKS 3
+#endif
+
 template <int ADT>
-__global__ void __launch_bounds__(32 * kTableWarps, 4) step_table_kernel(const StepArgs p) {
+__global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_table_kernel(const StepArgs p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const stage = reinterpret_cast<TableScratchWarp*>(smem_raw)[threadIdx.x >> 5].obs;
   const int lane = threadIdx.x & 31;
@@ -602,22 +690,50 @@ __global__ void __launch_bounds__(32 * kTableWarps, 4) step_table_kernel(const S
   float* const my_row = stage + lane * kObsDim;
   bool bulk_pending = false;
 
-  for (int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wg < n_groups; wg += warps_total) {
+  int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wg >= n_groups) return;
+  // the next group's state and action are in flight while this group's gathers are waited for
+  uint2 sv_n, mv_n;
+  int a_n;
+  auto fetch = [&](int group) {
+    const int ec = min((group << 5) + lane, p.n - 1);
+    sv_n = ld_stream(p.st_static + ec);
+    mv_n = ld_stream(p.st_mut + ec);
+    a_n = load_action<ADT>(p.action, ec);
+  };
+  fetch(wg);
+  for (; wg < n_groups; wg += warps_total) {
     const int base = wg << 5;
     const int e = base + lane;
     const bool valid = e < p.n;
-    const int ec = valid ? e : p.n - 1;
-    const uint2 sv = ld_stream(p.st_static + ec);
-    uint2 mv = ld_stream(p.st_mut + ec);
-    const int a = load_action<ADT>(p.action, ec);
+    const uint2 sv = sv_n;
+    uint2 mv = mv_n;
+    const int a = a_n;
     const int t_before = mv.y & 0xff;
     const bool canon = (mv.y >> 31) != 0;
     const Transition tr = advance(sv, mv, a);
-    if (valid) st_stream(p.st_mut + e, mv);
     const unsigned cv = sv.y;
     const unsigned sy = div_magic(sv.x & 0xffffffu, p.tb.magic_T);
     const unsigned yr = sy - div_magic(sy, p.tb.magic_Y) * static_cast<unsigned>(p.tb.Y);
     const bool fast = canon && t_before == t_table;
+    const unsigned fast_mask = __ballot_sync(kFull, fast);
+    // ---- every gather of the group is issued before anything waits on one ---------------------------
+    // (loads are unconditional -- an env off the fast path reads record 0 and ignores it -- so that no
+    // select sits between a load and the next one)
+    const unsigned zl = (yr * 10923u) >> 16;  // year / 6 (exact below 2^14)
+    const float4* zrec = p.tb.z_tab + (static_cast<size_t>(fast ? cv : 0u) * p.tb.z_lines + (fast ? zl : 0u)) * 8;
+    const float4 o0 = ldg_keep(zrec, keep);
+    const float2 o1 = __ldg(reinterpret_cast<const float2*>(zrec + 1));
+    const double2 z = __ldg(reinterpret_cast<const double2*>(zrec + 2) + (fast ? yr - zl * kZPerLine : 0u));
+    float4 rows[8];  // observation rows: 8 lanes copy one float32 row, four neighbouring envs per round
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int j = 4 * it + g;
+      const unsigned syj = __shfl_sync(kFull, sy, j);
+      rows[it] = __ldg(xobs_lane + static_cast<size_t>(((fast_mask >> j) & 1u) && !(W2A_TABLE_KO & 16) ? syj : 0u) * 8);
+    }
+    if (valid) st_stream(p.st_mut + e, mv);
+    if (wg + warps_total < n_groups) fetch(wg + warps_total);
     const bool write_obs = valid && !tr.done;
     const unsigned wmask = __ballot_sync(kFull, write_obs);
     if (bulk_pending) {  // the previous group's bulk store must have finished reading the staging buffer
@@ -626,14 +742,9 @@ __global__ void __launch_bounds__(32 * kTableWarps, 4) step_table_kernel(const S
       bulk_pending = false;
     }
     // ---- logits -------------------------------------------------------------------------------
-    const float4* wo = reinterpret_cast<const float4*>(p.tb.w + static_cast<size_t>(cv) * kWStride + kWOther);
-    const float4 o0 = ldg_keep(wo, keep), o1 = ldg_keep(wo + 1, keep);
-    double zb, ze;
-    if (fast) {
-      const double2 z = __ldg(p.tb.z_tab + static_cast<size_t>(cv) * p.tb.Y + yr);
-      zb = z.x;
-      ze = z.y;
-    } else {  // off-day or non-canonical env: straight from the tables, row staged by its own thread
+    double zb = z.x, ze = z.y;
+    float lag_b = o0.x, lag_e = o0.y, streak_b = o0.z, streak_e = o0.w, rem_b = o1.x, rem_e = o1.y;
+    if (!fast) {  // off-day or non-canonical env: straight from the tables, row staged by its own thread
       const double* xr = p.tb.x + static_cast<size_t>(tr.row) * kXStride;
       const float* wv = p.tb.w + static_cast<size_t>(cv) * kWStride;
       zb = __ldg(xr + 25) * static_cast<double>(__ldg(wv + 50));
@@ -645,42 +756,42 @@ __global__ void __launch_bounds__(32 * kTableWarps, 4) step_table_kernel(const S
         my_row[slot_of_feature(u)] = static_cast<float>(x);
       }
       my_row[27] = sig_to_obs(static_cast<float>(__ldg(xr + kXSig)));
+      zb += static_cast<double>(__ldg(wv + kWOther + 6));
+      ze += static_cast<double>(__ldg(wv + kWOther + 7));
+      lag_b = __ldg(wv + kWOther); lag_e = __ldg(wv + kWOther + 1);
+      streak_b = __ldg(wv + kWOther + 2); streak_e = __ldg(wv + kWOther + 3);
+      rem_b = __ldg(wv + kWOther + 4); rem_e = __ldg(wv + kWOther + 5);
     }
     {
       const double f_lag = static_cast<double>(tr.lag), f_streak = static_cast<double>(tr.streak),
                    f_rem = static_cast<double>(tr.rem);
-      zb += static_cast<double>(o1.z);
-      ze += static_cast<double>(o1.w);
-      zb = fma(f_lag, static_cast<double>(o0.x), zb);
-      ze = fma(f_lag, static_cast<double>(o0.y), ze);
-      zb = fma(f_streak, static_cast<double>(o0.z), zb);
-      ze = fma(f_streak, static_cast<double>(o0.w), ze);
-      zb = fma(f_rem, static_cast<double>(o1.x), zb);
-      ze = fma(f_rem, static_cast<double>(o1.y), ze);
+      zb = fma(f_lag, static_cast<double>(lag_b), zb);
+      ze = fma(f_lag, static_cast<double>(lag_e), ze);
+      zb = fma(f_streak, static_cast<double>(streak_b), zb);
+      ze = fma(f_streak, static_cast<double>(streak_e), ze);
+      zb = fma(f_rem, static_cast<double>(rem_b), zb);
+      ze = fma(f_rem, static_cast<double>(rem_e), ze);
     }
     if (valid) {
-      const double baseline = expit(zb);
-      const double eff = tr.act ? expit(ze) : 0.0;
-      __stcs(p.reward + e, static_cast<float>(kRewardScale * baseline * (1.0 - eff)));
-      p.terminated[e] = static_cast<uint8_t>(tr.done);
-      if (p.remaining) __stcs(p.remaining + e, tr.rem);
-      if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
+      const float rew = (W2A_TABLE_KO & 4) ? static_cast<float>(zb + ze) : step_reward(zb, ze, tr.act);
+      if (!(W2A_TABLE_KO & 2) || rew == 12345.f) {
+        __stcs(p.reward + e, rew);
+        p.terminated[e] = static_cast<uint8_t>(tr.done);
+        if (p.remaining) __stcs(p.remaining + e, tr.rem);
+        if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
+      }
     }
     __syncwarp();
-    // ---- observation rows: 8 lanes copy one float32 row, four neighbouring envs per round -----------
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int j = 4 * it + g;
-      const unsigned syj = __shfl_sync(kFull, sy, j);
-      const int fastj = __shfl_sync(kFull, static_cast<int>(fast), j);
-      if (fastj) {
-        const float4 v = __ldg(xobs_lane + static_cast<size_t>(syj) * 8);
+      if ((fast_mask >> j) & 1u) {
         float* st = stage + j * kObsDim + 4 * q;
-        st[0] = v.x;
+        st[0] = rows[it].x;
         if (q < 7) {
-          st[1] = v.y;
-          st[2] = v.z;
-          st[3] = v.w;
+          st[1] = rows[it].y;
+          st[2] = rows[it].z;
+          st[3] = rows[it].w;
         }
       }
     }
@@ -692,7 +803,8 @@ __global__ void __launch_bounds__(32 * kTableWarps, 4) step_table_kernel(const S
     fence_proxy_async_smem();
     __syncwarp();
     float* const ob = p.obs + static_cast<size_t>(base) * kObsDim;
-    if (wmask == kFull && obs_aligned) {
+    if ((W2A_TABLE_KO & 1) && stage[lane] != 12345.f) {
+    } else if (wmask == kFull && obs_aligned) {
       if (lane == 0) bulk_store(ob, stage, kObsBlockBytes, stream_out);
       bulk_pending = true;
     } else if (wmask != 0u) {
