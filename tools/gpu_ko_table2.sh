@@ -2,4 +2,5 @@
 for c in $@; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -DW2A_TABLE_KO=$c -I include -o /tmp/lib_ko$c.so weather2alert_b200/csrc/w2a.cu 2>/dev/null
   echo "KO=$c"; W2A_LIB_PATH=/tmp/lib_ko$c.so bash tools/gpu_warm_launches.sh --variant table | tail -2
+  W2A_LIB_PATH=/tmp/lib_ko$c.so python bench.py --variant table --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ms/step %.4f'%d['ms_per_step'])"
 done

@@ -1,0 +1,7 @@
+# usage: gpu_sweep_tb.sh minblocks...   table-build kernel launch bound: parity, warm per-kernel times, bench
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
+for c in $@; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -DW2A_TABLE_BUILD_MINBLOCKS=$c -I include -o /tmp/lib_tb$c.so weather2alert_b200/csrc/w2a.cu 2>/dev/null
+  echo "MINBLOCKS=$c"; W2A_LIB_PATH=/tmp/lib_tb$c.so bash tools/gpu_warm_launches.sh --variant table | tail -2
+  W2A_LIB_PATH=/tmp/lib_tb$c.so python bench.py --variant table --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ms/step %.4f'%d['ms_per_step'])"
+done

@@ -104,7 +104,9 @@ int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int varia
   int grid = 0;
   if (variant == W2A_STEP_TABLE) {
     // today's logit table for every (county, posterior sample, year), then the per-env kernel
-    w2a::logit_table_kernel<<<ctx->tb.Sw, w2a::kTableThreads, 0, st>>>(ctx->tb, a.st_mut);
+    const int table_tasks = ctx->tb.Sw * ((ctx->tb.P + 7) / 8) + (ctx->tb.Sw + 3) / 4;
+    const int table_grid = (table_tasks + w2a::kTableTaskWarps - 1) / w2a::kTableTaskWarps;
+    w2a::logit_table_kernel<<<table_grid, 32 * w2a::kTableTaskWarps, 0, st>>>(ctx->tb, a.st_mut);
     ctx->launches++;
     constexpr int kBlock = 32 * w2a::kTableWarps;
     int rc = grid_for(ctx, w2a::step_table_kernel<ADT>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);

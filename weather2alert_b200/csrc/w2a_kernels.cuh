@@ -554,112 +554,119 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
 // (same arithmetic as the THREAD kernel), so the result never depends on the envs being in
 // lock step -- only the speed does.
 // =========================================================================================
-#ifndef W2A_TABLE_KO  // experiments only (tools/gpu_ko_table.sh): knock parts of the kernel out, results become wrong
-#define W2A_TABLE_KO 0
-#endif
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))),
-               "l"(gmem_src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-constexpr int kTableThreads = 128;
-constexpr int kTableYears = 18;     // years per shared-memory pass (a multiple of kZPerLine)
-constexpr int kZPerLine = 6;        // (z_b, z_e) entries per 128-byte line, after the 32-byte head
-constexpr int kWsStride = 17;       // float4 per staged coefficient record: banks 4*p, conflict-free
-__global__ void __launch_bounds__(kTableThreads, 3) logit_table_kernel(const Tables tb, const uint2* st_mut) {
-  // day-rows [year][13 x double2]: positions (0,1) .. (22,23) and (significance code, gate)
-  __shared__ double2 xs[kTableYears][13];
-  __shared__ float4 ws[kTableThreads * kWsStride];
-  const int tid = threadIdx.x;
-  const int col = blockIdx.x;
+constexpr int kZPerLine = 6;     // (z_b, z_e) entries per 128-byte line, after the 32-byte head
+constexpr int kTableTaskWarps = 8;  // warps (= tasks) per CTA of logit_table_kernel
+#ifndef W2A_TABLE_BUILD_MINBLOCKS
+#define W2A_TABLE_BUILD_MINBLOCKS 3
+#endif
+
+// D(8x8) += A(8x4) * B(4x8) in float64 on the tensor cores (DMMA).  Fragments: A[lane/4][lane%4],
+// B[lane%4][lane/4], C/D[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// The table build is a small float64 GEMM per county -- Z[(p, head), y] = W[(p, head), 0..23] .
+// X[y, 0..23]^T, plus the bias and (for z_e) the gate column -- so it runs on the FP64 tensor path:
+// one warp per task = (coefficient column, block of 8 posterior samples): 6 k-steps x 2 heads per
+// tile of 8 years of m8n8k4.  Operands come straight from the L2-resident tables; everything that
+// depends on the task index alone (coefficients, line heads) is requested before the first wait,
+// and the day-rows (which need the day and the county: one dependent round trip) of the first two
+// year tiles right after.  The leading tasks write the float32 observation rows instead.
+__global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCKS)
+    logit_table_kernel(const Tables tb, const uint2* st_mut) {
+  const int lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int mtiles = (tb.P + 7) >> 3;
+  const int n_row_tasks = (tb.Sw + 3) >> 2;  // leading tasks: the observation rows of four columns each
+  const int task = blockIdx.x * kTableTaskWarps + (threadIdx.x >> 5) - n_row_tasks;
+  const unsigned t_word = __ldg(&st_mut[0].y);
+  if (task < 0) {
+    // ---- observation rows (slot order, float32) of day t for up to four coefficient columns ----
+    const int t = min(static_cast<int>(t_word & 0xffu), tb.T - 1);
+    if (task == -n_row_tasks && lane == 0) *tb.t_cell = t;
+    const int pos = lane < 23 ? lane : lane == 26 ? 23 : lane == 27 ? kXSig : -1;
+    for (int c = 0; c < 4; ++c) {
+      const int col = (task + n_row_tasks) * 4 + c;
+      if (col >= tb.Sw) break;
+      const int s = __ldg(tb.col_to_loc + col);
+      if (s < 0) continue;
+      const double* xrow = tb.x + (static_cast<size_t>(s) * tb.Y * tb.T + t) * kXStride + max(pos, 0);
+      for (int y0 = 0; y0 < tb.Y; y0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          v[j] = y0 + j < tb.Y ? __ldg(xrow + static_cast<size_t>(y0 + j) * tb.T * kXStride) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float f = pos >= 0 ? static_cast<float>(v[j]) : 0.f;
+          if (lane == 27) f = sig_to_obs(f);
+          if (y0 + j < tb.Y) tb.xobs_t[static_cast<size_t>(s * tb.Y + y0 + j) * 32 + lane] = f;
+        }
+      }
+    }
+    return;
+  }
+  if (task >= tb.Sw * mtiles) return;
+  const int col = task / mtiles, mt = task - col * mtiles;
   const int s = __ldg(tb.col_to_loc + col);
-  const int t = min(static_cast<int>(__ldg(&st_mut[0].y) & 0xffu), tb.T - 1);
-  if (col == 0 && tid == 0) *tb.t_cell = t;
+  const int p = mt * 8 + gid;  // this lane's row of A and C
+  const bool p_ok = p < tb.P;
+  const float2* wrec = reinterpret_cast<const float2*>(tb.w + static_cast<size_t>(col * tb.P + min(p, tb.P - 1)) * kWStride);
+  float2 wv[6];  // A fragments of the two heads: coefficient pair of record position 4*ks + tig
+#pragma unroll
+  for (int ks = 0; ks < 6; ++ks) wv[ks] = __ldg(wrec + 4 * ks + tig);
+  const float2 bias = __ldg(wrec + 31);
+  float4 h = __ldg(reinterpret_cast<const float4*>(wrec) + 14 + (tig & 1));  // lag, streak | remaining budget, bias
   if (s < 0) return;
-  for (int p0 = 0; p0 < tb.P; p0 += kTableThreads) {
-    const int np = min(kTableThreads, tb.P - p0);
-    // the county's coefficient records and (per pass) day-rows go global -> shared memory as
-    // asynchronous 16-byte copies: all in flight at once, no staging registers
-    __syncthreads();  // earlier readers of ws are done
-    {
-      const float4* wsrc = reinterpret_cast<const float4*>(tb.w + static_cast<size_t>(col * tb.P + p0) * kWStride);
-      for (int i = tid; i < np * 16; i += kTableThreads) cp_async16(&ws[(i >> 4) * kWsStride + (i & 15)], wsrc + i);
-    }
-    bool w_staged = false;
-    double wb[26], we[26];
-    float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 head2 = make_float2(0.f, 0.f);
-    double bias_b = 0.0, bias_e = 0.0;
-    for (int y0 = 0; y0 < tb.Y; y0 += kTableYears) {
-      const int ny = min(kTableYears, tb.Y - y0);
-      if (y0 > 0) __syncthreads();  // earlier readers of xs are done
-      for (int i = tid; i < ny * 13; i += kTableThreads) {
-        const int y = i / 13, k = i - y * 13;
-        cp_async16(&xs[y][k], reinterpret_cast<const double2*>(
-                                  tb.x + (static_cast<size_t>(s * tb.Y + y0 + y) * tb.T + t) * kXStride) + k);
-      }
-      cp_async_wait_all();
-      __syncthreads();
-      if (p0 == 0) {  // observation rows of the county's years, slot order, float32
-        for (int i = tid; i < ny * 32; i += kTableThreads) {
-          const int y = i >> 5, slot = i & 31;
-          const double* xr = reinterpret_cast<const double*>(xs[y]);
-          float v = 0.f;
-          if (slot < 23) v = static_cast<float>(xr[slot]);
-          else if (slot == 26) v = static_cast<float>(xr[23]);
-          else if (slot == 27) v = sig_to_obs(static_cast<float>(xr[kXSig]));
-          tb.xobs_t[static_cast<size_t>(s * tb.Y + y0 + y) * 32 + slot] = v;
-        }
-      }
-      if (tid < np) {
-        if (!w_staged) {  // this thread's sample: both heads' coefficients to float64 registers
+  const int t = min(static_cast<int>(t_word & 0xffu), tb.T - 1);
+  float4* rec = tb.z_tab + static_cast<size_t>(col * tb.P + p) * (tb.z_lines * 8);
+  const double* xday = tb.x + (static_cast<size_t>(s) * tb.Y * tb.T + t) * kXStride;
+  const size_t ystride = static_cast<size_t>(tb.T) * kXStride;
+  // year tiles of 8: B fragments x[y0 + gid][4*ks + tig] and, for this lane's two columns of C,
+  // the gate x[y][25] (coefficients (0, 1): added to z_e as it is)
+  auto load_b = [&](double (&xb)[6], double (&gate)[2], int y0) {
+    const int yb = min(y0 + gid, tb.Y - 1);  // columns past Y are computed on a copy of the last year, never stored
 #pragma unroll
-          for (int k = 0; k < 13; ++k) {  // floats 4k..4k+3 = (b,e) of positions 2k, 2k+1 (24: zeros, 25: gate (0,1))
-            const float4 v = ws[tid * kWsStride + k];
-            wb[2 * k] = v.x; we[2 * k] = v.y; wb[2 * k + 1] = v.z; we[2 * k + 1] = v.w;
-          }
-          head = ws[tid * kWsStride + 14];  // lag (b,e), streak (b,e)
-          const float4 tail = ws[tid * kWsStride + 15];  // remaining budget (b,e), bias (b,e)
-          head2 = make_float2(tail.x, tail.y);
-          bias_b = tail.z;
-          bias_e = tail.w;
-        }
-        // logits, two years at a time (four independent accumulation chains); the day-rows are
-        // broadcast 128-bit shared-memory reads
-        float4* rec = tb.z_tab + static_cast<size_t>(col * tb.P + p0 + tid) * (tb.z_lines * 8);
-        for (int y = 0; y < ((W2A_TABLE_KO & 64) ? 1 : ny); y += 2) {
-          const int y1 = min(y + 1, ny - 1);
-          double zb0 = 0.0, ze0 = 0.0, zb1 = 0.0, ze1 = 0.0;
+    for (int ks = 0; ks < 6; ++ks) xb[ks] = __ldg(xday + yb * ystride + 4 * ks + tig);
 #pragma unroll
-          for (int k = 0; k < 13; ++k) {
-            const double2 xa = xs[y][k], xb = xs[y1][k];
-            if (k < 12) {
-              zb0 = fma(xa.x, wb[2 * k], zb0); ze0 = fma(xa.x, we[2 * k], ze0);
-              zb1 = fma(xb.x, wb[2 * k], zb1); ze1 = fma(xb.x, we[2 * k], ze1);
-              zb0 = fma(xa.y, wb[2 * k + 1], zb0); ze0 = fma(xa.y, we[2 * k + 1], ze0);
-              zb1 = fma(xb.y, wb[2 * k + 1], zb1); ze1 = fma(xb.y, we[2 * k + 1], ze1);
-            } else {  // (significance code, gate): only the gate enters, with its (0, 1) coefficients
-              zb0 = fma(xa.y, wb[25], zb0); ze0 = fma(xa.y, we[25], ze0);
-              zb1 = fma(xb.y, wb[25], zb1); ze1 = fma(xb.y, we[25], ze1);
-            }
-          }
-          const int ya = y0 + y, yb = y0 + y1;
-          double2* za = reinterpret_cast<double2*>(rec + (ya / kZPerLine) * 8 + 2) + ya % kZPerLine;
-          double2* zb = reinterpret_cast<double2*>(rec + (yb / kZPerLine) * 8 + 2) + yb % kZPerLine;
-          if ((W2A_TABLE_KO & 128) && zb0 != 12345.0) continue;
-          *za = make_double2(zb0 + bias_b, ze0 + bias_e);
-          if (y1 != y) *zb = make_double2(zb1 + bias_b, ze1 + bias_e);
-        }
-        // line heads of the lines this pass touched (kTableYears is a multiple of kZPerLine)
-        for (int l = y0 / kZPerLine; l * kZPerLine < y0 + ny; ++l) {
-          rec[l * 8] = head;
-          rec[l * 8 + 1] = make_float4(head2.x, head2.y, 0.f, 0.f);
-        }
-      }
-      w_staged = true;
+    for (int i = 0; i < 2; ++i) gate[i] = __ldg(xday + min(y0 + 2 * tig + i, tb.Y - 1) * ystride + 25);
+  };
+  double xb0[6], xb1[6], g0[2], g1[2];
+  load_b(xb0, g0, 0);
+  load_b(xb1, g1, 8);
+  double ab[6], ae[6];
+#pragma unroll
+  for (int ks = 0; ks < 6; ++ks) {
+    ab[ks] = wv[ks].x;
+    ae[ks] = wv[ks].y;
+  }
+  auto tile = [&](const double (&xb)[6], const double (&gate)[2], int y0) {
+    double cb[2] = {bias.x, bias.x}, ce[2] = {bias.y + gate[0], bias.y + gate[1]};
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) {
+      dmma_884(cb, ab[ks], xb[ks]);
+      dmma_884(ce, ae[ks], xb[ks]);
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int y = y0 + 2 * tig + i;  // this lane's columns of C
+      if (p_ok && y < tb.Y)
+        reinterpret_cast<double2*>(rec + (y / kZPerLine) * 8 + 2)[y % kZPerLine] = make_double2(cb[i], ce[i]);
+    }
+  };
+  tile(xb0, g0, 0);
+  if (tb.Y > 8) tile(xb1, g1, 8);
+  for (int y0 = 16; y0 < tb.Y; y0 += 8) {
+    load_b(xb0, g0, y0);
+    tile(xb0, g0, y0);
+  }
+  if (p_ok && tig < 2) {  // line heads: the six agent coefficients, 24 bytes + 8 zero
+    if (tig == 1) h.z = h.w = 0.f;
+    for (int l = 0; l < tb.z_lines; ++l) rec[l * 8 + tig] = h;
   }
 }
 
@@ -669,6 +676,9 @@ struct __align__(128) TableScratchWarp {
 constexpr int kTableWarps = 8;
 constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScratchWarp));
 
+#ifndef W2A_TABLE_KO  // experiments only (tools/gpu_ko_table.sh): knock parts of the kernel out, results become wrong
+#define W2A_TABLE_KO 0
+#endif
 #ifndef W2A_TABLE_MINBLOCKS
 #define W2A_TABLE_MINBLOCKS 3
 #endif
