@@ -194,6 +194,11 @@ def run_ours(args):
     T = int(store.n_days.max())
     variant = {"auto": _lib.STEP_AUTO, "thread": _lib.STEP_THREAD, "coop": _lib.STEP_COOP,
                "table": _lib.STEP_TABLE}[args.variant]
+    if variant == _lib.STEP_AUTO:  # what HeatAlertVectorEnv does: the logit table for big non-augmented env sets
+        variant = core.choose_variant(n, canonical=not wl["augment"])
+    kernel_name = {_lib.STEP_TABLE: "logit_table_kernel + step_table_kernel", _lib.STEP_COOP: "step_coop_kernel",
+                   _lib.STEP_THREAD: "step_thread_kernel"}.get(
+        variant, "step_coop_kernel" if n >= 2048 else "step_thread_kernel")
 
     state = core.alloc_state(n)
     obs = torch.zeros((n, 29), dtype=torch.float32, device=dev)
@@ -271,7 +276,8 @@ def run_ours(args):
     clocks.stop_flag.set()
     launches = core.launch_count - launches0
     if use_graph:
-        launches += (K // T) * (T + 1)  # kernels replayed from the graph are not seen by the C-side counter
+        per_step = 2 if variant == _lib.STEP_TABLE else 1  # TABLE = table build + per-env kernel
+        launches += (K // T) * (T * per_step + 1)  # kernels replayed from the graph are not seen by the C-side counter
     ms = ev0.elapsed_time(ev1)
     ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -422,8 +428,8 @@ def run_ours(args):
                    "counties": S_COUNTIES, "years": N_YEARS, "days": T, "posterior_samples": P_SAMPLES,
                    "weights": "linear-format synthetic (nn_* checkpoints share the layout and the path)",
                    "augment": wl["augment"],
-                   "mode": "one CUDA graph per summer (153 step launches + reset)" if use_graph else "per-step launches",
-                   "locality": args.locality, "variant": args.variant,
+                   "mode": "one CUDA graph per summer (153 steps + reset)" if use_graph else "per-step launches",
+                   "locality": args.locality, "variant": args.variant, "kernel": kernel_name,
                    "parallelism": f"env-sharded x{world}, no step-time collective",
                    "l2": "per-step streaming traffic (151 B x envs) exceeds the 126 MB L2 for >= 2^20 envs; "
                          "tables (feature rows of the day + coefficients) are meant to stay L2-resident"},
@@ -433,7 +439,7 @@ def run_ours(args):
         "e2e": e2e,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "bytes_per_env_step": BYTES_STREAMING, "peak_source": peak_src,
-                     "kernel": "step_coop_kernel" if (variant == _lib.STEP_COOP or (variant == 0 and n >= 2048)) else "step_thread_kernel",
+                     "kernel": kernel_name,
                      "note": "achieved = streaming bytes (HBM-mandatory) x envs / mean step time over the timed region"},
         "roofline_canonical_466B": {"achieved": ach_c, "frac": ach_c / peak,
                                     "note": "SURVEY 8(d) canonical 466 B/env-step; includes table gathers served from L2"},

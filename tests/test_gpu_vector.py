@@ -231,3 +231,32 @@ def test_reference_rng_reset_equals_independent_single_envs(golden):
             o, r, d, _, inf = e.step(int(a[i]))
             np.testing.assert_array_equal(obs[i].cpu().numpy().view(np.int32), o.view(np.int32))
             assert r == float(rew[i]) and d == bool(term[i]) and inf["at_budget"] == bool(info["at_budget"][i])
+
+
+def test_vector_env_auto_variant_picks_table(golden, monkeypatch):
+    """AUTO above the C ABI: the per-step logit table for large batches of envs on their own county's
+    coefficients, COOP/THREAD otherwise -- and the choice never changes a result (ragged summers make
+    the envs fall out of lock step after the first autoreset: those take the table kernel's direct path)."""
+    from weather2alert_b200 import HeatAlertVectorEnv, _lib
+    from weather2alert_b200.core import HeatAlertCore
+
+    store, weights = golden.store(), golden.weights("std")
+    n = 257
+    small = HeatAlertVectorEnv(n, weights=weights, store=store, seed=5)
+    small.reset()
+    assert small._variant() == _lib.STEP_AUTO  # below TABLE_MIN_ENVS
+    monkeypatch.setattr(HeatAlertCore, "TABLE_MIN_ENVS", 1)
+    assert small._variant() == _lib.STEP_TABLE
+    aug = HeatAlertVectorEnv(n, weights=weights, store=store, seed=5, similar_climate_counties=True)
+    aug.reset()
+    assert aug._variant() == _lib.STEP_AUTO  # similar-county substitution: not the county's own column
+    forced = HeatAlertVectorEnv(n, weights=weights, store=store, seed=5, step_variant=_lib.STEP_COOP)
+    forced.reset()
+    rng = np.random.default_rng(3)
+    for i in range(200):
+        act = torch.from_numpy(rng.random(n) < 0.3).cuda()
+        o1, r1, t1, _, i1 = small.step(act)
+        o2, r2, t2, _, i2 = forced.step(act)
+        assert torch.equal(o1.view(torch.int32), o2.view(torch.int32)) and torch.equal(t1, t2), f"step {i}"
+        assert torch.allclose(r1, r2, rtol=1e-6, atol=1e-10)
+    assert (_lib.STEP_TABLE in {k[1] for k in small._bound}) and (_lib.STEP_COOP in {k[1] for k in forced._bound})

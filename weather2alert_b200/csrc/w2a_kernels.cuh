@@ -676,9 +676,6 @@ struct __align__(128) TableScratchWarp {
 constexpr int kTableWarps = 8;
 constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScratchWarp));
 
-#ifndef W2A_TABLE_KO  // experiments only (tools/gpu_ko_table.sh): knock parts of the kernel out, results become wrong
-#define W2A_TABLE_KO 0
-#endif
 #ifndef W2A_TABLE_MINBLOCKS
 #define W2A_TABLE_MINBLOCKS 3
 #endif
@@ -740,7 +737,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     for (int it = 0; it < 8; ++it) {
       const int j = 4 * it + g;
       const unsigned syj = __shfl_sync(kFull, sy, j);
-      rows[it] = __ldg(xobs_lane + static_cast<size_t>(((fast_mask >> j) & 1u) && !(W2A_TABLE_KO & 16) ? syj : 0u) * 8);
+      rows[it] = __ldg(xobs_lane + static_cast<size_t>(((fast_mask >> j) & 1u) ? syj : 0u) * 8);
     }
     if (valid) st_stream(p.st_mut + e, mv);
     if (wg + warps_total < n_groups) fetch(wg + warps_total);
@@ -783,13 +780,10 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
       ze = fma(f_rem, static_cast<double>(rem_e), ze);
     }
     if (valid) {
-      const float rew = (W2A_TABLE_KO & 4) ? static_cast<float>(zb + ze) : step_reward(zb, ze, tr.act);
-      if (!(W2A_TABLE_KO & 2) || rew == 12345.f) {
-        __stcs(p.reward + e, rew);
-        p.terminated[e] = static_cast<uint8_t>(tr.done);
-        if (p.remaining) __stcs(p.remaining + e, tr.rem);
-        if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
-      }
+      __stcs(p.reward + e, step_reward(zb, ze, tr.act));
+      p.terminated[e] = static_cast<uint8_t>(tr.done);
+      if (p.remaining) __stcs(p.remaining + e, tr.rem);
+      if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
     }
     __syncwarp();
 #pragma unroll
@@ -813,8 +807,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     fence_proxy_async_smem();
     __syncwarp();
     float* const ob = p.obs + static_cast<size_t>(base) * kObsDim;
-    if ((W2A_TABLE_KO & 1) && stage[lane] != 12345.f) {
-    } else if (wmask == kFull && obs_aligned) {
+    if (wmask == kFull && obs_aligned) {
       if (lane == 0) bulk_store(ob, stage, kObsBlockBytes, stream_out);
       bulk_pending = true;
     } else if (wmask != 0u) {

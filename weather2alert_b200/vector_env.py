@@ -107,6 +107,7 @@ class HeatAlertVectorEnv:
         self._rem = torch.zeros(n, dtype=torch.int32, device=dev)
         self._atb = torch.zeros(n, dtype=torch.bool, device=dev)
         self._bound = {}
+        self._canonical = False  # every env's coefficient column is its own county (set by each draw)
         # rollout statistics a la AlertLoggingCallback (callbacks.py:63-74); `stats.reduce()` all-reduces them
         self.stats = None
         if track_stats:
@@ -129,6 +130,7 @@ class HeatAlertVectorEnv:
         n, dev, o = self.num_envs, self.device, self._reset_opts
         sp = self.sampler
         if "index_streams" in o:
+            self._canonical = False  # caller-chosen (county, column) pairs: not known to be the county's own
             src = o["index_streams"]
             s = {k: torch.as_tensor(np.ascontiguousarray(src[k], dtype=np.int32)).to(dev)
                  for k in ("loc", "year", "coef_col", "coef_idx")}
@@ -147,6 +149,7 @@ class HeatAlertVectorEnv:
                 raise KeyError((self.store.fips[int(src["loc"][bad])], self.store.years[int(src["year"][bad])]))
             return s
         augment = o.get("similar_climate_counties", self.similar_climate_counties)
+        self._canonical = not augment
         location = o.get("location")
         if o.get("reference_rng", False):
             # what gymnasium.vector.SyncVectorEnv([HeatAlertEnv]*N).reset(seed=s) does: env i seeds its
@@ -267,6 +270,14 @@ class HeatAlertVectorEnv:
         self._next_term = int(self._term_at.min())  # one small sync per reset, only for ragged summers
 
     # ---- step -----------------------------------------------------------------------------------
+    def _variant(self) -> int:
+        """The step kernel for the current episodes: the caller's choice, or (AUTO) the per-step logit
+        table when every env steps on its own county's coefficients and the batch is large enough to pay
+        for building the table (`HeatAlertCore.choose_variant`)."""
+        if self.step_variant != _lib.STEP_AUTO:
+            return self.step_variant
+        return self.core.choose_variant(self.num_envs, canonical=self._canonical)
+
     def step(self, actions: torch.Tensor):
         if self._next_term is None:
             raise RuntimeError("call reset() before step()")
@@ -278,11 +289,12 @@ class HeatAlertVectorEnv:
             actions = actions.view(torch.uint8)
         if not actions.is_contiguous():
             actions = actions.contiguous()
-        fn = self._bound.get(actions.dtype)
+        variant = self._variant()
+        fn = self._bound.get((actions.dtype, variant))
         if fn is None:
-            fn = self._bound[actions.dtype] = self.core.bind_step(
+            fn = self._bound[(actions.dtype, variant)] = self.core.bind_step(
                 self._state, self._obs, self._reward, self._term.view(torch.uint8), self._rem,
-                self._atb.view(torch.uint8), variant=self.step_variant, action_dtype=actions.dtype)
+                self._atb.view(torch.uint8), variant=variant, action_dtype=actions.dtype)
         fn(actions)
         if self.stats is not None:
             self.stats.update(actions, self._reward, self._term, self._atb)
@@ -381,7 +393,7 @@ class GraphedRollout:
         self.returns = torch.zeros(n, dtype=torch.float64, device=dev)
         self._act = torch.zeros(n, dtype=torch.uint8, device=dev)
         step = env.core.bind_step(env._state, env._obs, env._reward, env._term.view(torch.uint8), env._rem,
-                                  env._atb.view(torch.uint8), variant=env.step_variant, action_dtype=torch.uint8)
+                                  env._atb.view(torch.uint8), variant=env._variant(), action_dtype=torch.uint8)
 
         def body():
             self.returns.zero_()
