@@ -53,8 +53,10 @@ extern "C" {
 #define W2A_STEP_AUTO 0   /* THREAD below 2048 envs, COOP from there on */
 #define W2A_STEP_THREAD 1 /* one thread per env (small batches, reference kernel) */
 #define W2A_STEP_COOP 2   /* 8 lanes per env: whole-line gathers, float64 fold in shared memory, TMA obs store */
-#define W2A_STEP_TABLE 3  /* today's logits of every (county, sample, year) once per step, then a 16-byte
-                             lookup per env; for big non-augmented env sets; needs w2a_set_county_map */
+#define W2A_STEP_TABLE 3  /* two launches: today's logits of every (county, sample, year) once (a float64 GEMM per
+                             county on the FP64 tensor path), then one 128-byte record + one observation row per
+                             env; for big non-augmented env sets in lock step; needs w2a_set_county_map; envs the
+                             table does not cover are computed directly, so results never depend on the variant */
 
 /* per-env budget value meaning "use the episode's historical budget"
  * (env.py:167-170: `self.ep["remaining_budget"].iloc[0]`). */
@@ -97,7 +99,7 @@ int w2a_set_coefs(w2a_ctx* ctx, const float* w, int P, int S_w);
 /* Optional: tell the library which feature-store county each coefficient column belongs to
  * (`fips_list[col]` -> index into the feature store, -1 = not in the store; the reference
  * keeps both keyed by FIPS string, env.py:75,121,127).  Enables W2A_STEP_TABLE; the context
- * allocates S_w*P*Y*16 + S*Y*128 bytes of scratch for the per-step tables.  Call after
+ * allocates S_w*P*ceil(Y/6)*128 + S*Y*128 bytes of scratch for the per-step tables.  Call after
  * w2a_set_features / w2a_set_coefs and before w2a_reset (the reset marks the envs whose column
  * is their own county).  `col_to_loc` is dev int32 [S_w], referenced, not copied. */
 int w2a_set_county_map(w2a_ctx* ctx, const int32_t* col_to_loc);

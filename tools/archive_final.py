@@ -45,15 +45,19 @@ json.dump({"workload": "cfg3_1m", "envs": 1048576, "kernel": "step_table_kernel"
            "dram_bytes_read": rd, "dram_bytes_written": wr,
            "source": f"profiles/{rnd}/final_step_table_raw.csv (ncu --set full, one launch)"},
           open(os.path.join(REPO, "profiles", "traffic.json"), "w"), indent=1)
-for name, rr in [(x[hdr.index("Kernel Name")][:40], x) for x in rows[2:]] + (
-        [(x[rows_coop[0].index("Kernel Name")][:40], x) for x in rows_coop[2:]] if rows_coop else []):
-    print("==", name)
-    r = rr
-    for k in ("gpu__time_duration.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
-              "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
-              "lts__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-              "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct"):
-        print(k, r[hdr.index(k)], units[hdr.index(k)])
+for rws in (rows, rows_coop):
+    if not rws:
+        continue
+    h, u = rws[0], rws[1]
+    for r in rws[2:]:
+        print("==", r[h.index("Kernel Name")][:40])
+        for k in ("gpu__time_duration.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                  "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+                  "lts__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                  "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                  "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if k in h:
+                print(k, r[h.index(k)], u[h.index(k)])
 print("dram read/write MB", rd / 1e6, wr / 1e6)
 lrows = list(csv.reader(open(os.path.join(dst, "final_launches.csv"))))
 hi = next(i for i, x in enumerate(lrows) if x and x[0] == "ID")
@@ -63,8 +67,11 @@ for x in lrows[hi + 1:]:
     if len(x) > mv:
         agg[x[kn].split("(")[0][-50:]][0] += 1
         agg[x[kn].split("(")[0][-50:]][1] += float(x[mv])
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:4]:
-    print(v[0], "x", k, round(v[1] / v[0] / 1e3, 1), "us avg")
+summary = ["ncu launch list of `bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline` (cold caches, serialised):"]
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:6]:
+    summary.append(f"{v[0]:4d} x {k:55s} {v[1] / v[0] / 1e3:8.1f} us avg {v[1] / 1e3:10.1f} us total")
+open(os.path.join(dst, "final_launches_summary.txt"), "w").write("\n".join(summary) + "\n")
+print("\n".join(summary))
 for f in sorted(os.listdir(dst)):
     if f.startswith("final_bench_") and f.endswith(".json"):
         d = json.loads(open(os.path.join(dst, f)).read().strip().splitlines()[-1])
