@@ -156,6 +156,19 @@ int w2a_step(w2a_ctx* ctx, void* stream, int64_t n, const void* action, int acti
 int w2a_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, const uint8_t* actions,
                 uint64_t seed, float p_alert, void* state, double* ep_return, double* stats);
 
+/* The same loop with the agent inside the launch (`a = policy(obs); env.step(a)`, env.py:273-276 with a
+ * policy in place of `action_space.sample()`): a logistic policy on the 29-slot observation,
+ *   logit = sum_s policy[s] * obs[s] (s != 27, the significance label) + policy[29],
+ * deterministic (action = logit > 0) or stochastic (action = hash(seed, env, step) < sigmoid(logit) * 2^32,
+ * the counter-based stream of w2a_rollout).  The observation is the one the reference agent holds before
+ * acting: the first observation of the reset, then what each step returned (row of the day just stepped,
+ * agent slots after the action; env.py:186-195, quirk Q1), in float64.  Only envs at the start of a summer
+ * (fresh from w2a_reset) take part; others are left untouched.
+ *   policy   dev float64 [W2A_POLICY_LEN] */
+#define W2A_POLICY_LEN 30
+int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const double* policy, int stochastic,
+                       uint64_t seed, void* state, double* ep_return, double* stats);
+
 /* ---- host-buffer entry points: the call a CPU-side RL loop makes ------------------
  * The context owns a device-resident env set; every call copies its inputs from and its
  * outputs to HOST memory (pinned for full PCIe speed), pipelined in chunks over several

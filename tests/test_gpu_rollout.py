@@ -177,3 +177,80 @@ def test_rollout_at_baseline_size_matches_stepping():
     assert torch.allclose(ret, total, rtol=2e-6, atol=0)  # float32 rounding and the float32 sigmoid (<= 3e-7) of each stepped reward
     assert float(stats[0]) == n and float(stats[3]) == 153 * n
     assert float(stats[1]) == pytest.approx(float(ret.sum()), rel=1e-9)
+
+
+@pytest.mark.parametrize("stochastic", [False, True])
+@pytest.mark.parametrize("n", [1, 5, 1031])
+def test_policy_rollout_matches_the_oracle_loop(n, stochastic):
+    """`w2a_rollout_policy`: the agent inside the launch.  The oracle plays `a = policy(obs); obs, r = step(a)`
+    (env.py:273-276 with a logistic policy on the float64 observation, significance slot skipped); returns,
+    final state and the callback counts must agree."""
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200.core import HeatAlertCore
+    from weather2alert_b200.distributed import STAT_NAMES, rollout_hash, rollout_threshold
+
+    store, weights, idx = _case(300 + n, n)
+    core = HeatAlertCore(store, weights, "cuda:0")
+    d = {k: _dev(v) for k, v in idx.items()}
+    rng = np.random.default_rng(17 + n)
+    theta = rng.normal(0.0, 0.4, 30)
+    theta[6] = 0.0       # dos runs to 152: keep the logit in a range where both actions occur
+    theta[25] = 0.15     # remaining budget
+    theta[27] = 123.0    # the significance slot must be ignored
+    theta[29] = -0.5
+    use = np.array([s != 27 for s in range(29)])
+    seed = 4242
+
+    st = core.alloc_state(n)
+    obs0 = torch.zeros((n, 29), device="cuda")
+    core.reset(st, obs0, d["loc"], d["year"], d["coef_col"], d["coef_idx"], budget=d["budget"])
+    ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    stats = torch.zeros(15, dtype=torch.float64, device="cuda")
+    core.rollout_policy(st, 153, ret, _dev(theta), stochastic=stochastic, seed=seed, stats=stats)
+
+    ost, obs = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"], idx["coef_col"],
+                               idx["coef_idx"], idx["budget"])
+    obs = obs.copy()
+    ret_ref = np.zeros(n)
+    alive = np.ones(n, bool)
+    n_steps = alerts = refused = 0
+    acts_played = np.zeros((153, n), np.uint8)
+    for k in range(153):
+        logit = obs[:, use] @ theta[:29][use] + theta[29]
+        if stochastic:
+            p = 1.0 / (1.0 + np.exp(-logit))
+            a = rollout_hash(seed, np.arange(n), [k])[0] < rollout_threshold(p)
+        else:
+            a = logit > 0.0
+        acts_played[k] = a
+        before = ost["budget"] - ost["hist"].sum(axis=1)
+        o, r, dn, rem, atb = orc.batch_step(store.feat, store.sig_code, weights.coef, ost, a.astype(np.uint8))
+        ret_ref += np.where(alive, r, 0.0)
+        n_steps += int(alive.sum())
+        alerts += int(((before - rem) * alive).sum())
+        refused += int((a & atb & alive).sum())
+        obs = np.where((alive & ~dn)[:, None], o, obs)  # on and after the last day the old observation stands
+        alive &= ~dn
+    assert not alive.any()
+    np.testing.assert_allclose(ret.cpu().numpy(), ret_ref, rtol=1e-9, atol=1e-12)
+    s = dict(zip(STAT_NAMES, stats.cpu().tolist()))
+    assert s["episodes"] == n and s["steps"] == n_steps
+    assert s["alerts"] == alerts and s["refused_at_budget"] == refused
+    if n > 100:
+        assert 0 < alerts < n_steps and refused > 0  # the policy really decides both ways, and runs into budgets
+    # the state the launch leaves = the state after stepping the same actions
+    st2 = core.alloc_state(n)
+    obs2 = torch.zeros((n, 29), device="cuda")
+    core.reset(st2, obs2, d["loc"], d["year"], d["coef_col"], d["coef_idx"], budget=d["budget"])
+    ret2 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    core.rollout(st2, 153, ret2, actions=_dev(acts_played))
+    assert torch.equal(st, st2)
+    # mid-summer envs are left alone
+    st3 = core.alloc_state(n)
+    core.reset(st3, obs2, d["loc"], d["year"], d["coef_col"], d["coef_idx"], budget=d["budget"])
+    core.rollout(st3, 3, ret2, actions=_dev(acts_played[:3]))
+    keep = st3.clone()
+    r3 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    core.rollout_policy(st3, 153, r3, _dev(theta), stochastic=stochastic, seed=seed)
+    mid = torch.from_numpy(store.n_days[idx["loc"], idx["year"]] > 3).cuda()
+    assert torch.equal(st3.view(2, n, 8)[:, mid], keep.view(2, n, 8)[:, mid]) and not r3[mid].any()

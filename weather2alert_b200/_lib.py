@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("W2A_LIB_PATH") or os.path.join(_HERE, "libw2a.so")
 W2A_OK = 0
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 STEP_AUTO, STEP_THREAD, STEP_COOP, STEP_TABLE = 0, 1, 2, 3
+POLICY_LEN = 30  # W2A_POLICY_LEN: one weight per observation slot + bias
 BUDGET_DEFAULT = -(2**31)
 OBS_DIM = 29
 
@@ -32,6 +33,7 @@ SIGNATURES = {
     "w2a_reset": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "w2a_step": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int]),
     "w2a_rollout": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_uint64, C.c_float, _P, _P, _P]),
+    "w2a_rollout_policy": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int, C.c_uint64, _P, _P, _P]),
     "w2a_host_envs_create": (C.c_int, [_P, C.c_int64]),
     "w2a_host_envs_destroy": (C.c_int, [_P]),
     "w2a_reset_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -158,6 +158,18 @@ class HeatAlertCore:
         _lib.check(self._lib.w2a_rollout(self.ctx, self._stream(), n, int(steps), _ptr(actions), int(seed) & (2**64 - 1),
                                          float(p_alert), _ptr(state), _ptr(ep_return), _ptr(stats)), self.ctx)
 
+    def rollout_policy(self, state, steps: int, ep_return, policy, stochastic: bool = False, seed: int = 0, stats=None):
+        """Episode-fused rollout with a logistic policy evaluated inside the launch (`w2a_rollout_policy`):
+        `policy` = float64 [30] CUDA tensor, one weight per observation slot (slot 27 ignored) + bias."""
+        n = ep_return.numel()
+        self._check_dev("state", state, torch.uint8, n * 16)
+        self._check_dev("ep_return", ep_return, torch.float64, n)
+        self._check_dev("stats", stats, torch.float64, 15)
+        self._check_dev("policy", policy, torch.float64, _lib.POLICY_LEN)
+        _lib.check(self._lib.w2a_rollout_policy(self.ctx, self._stream(), n, int(steps), _ptr(policy), int(bool(stochastic)),
+                                                int(seed) & (2**64 - 1), _ptr(state), _ptr(ep_return), _ptr(stats)),
+                   self.ctx)
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.w2a_launch_count(self.ctx))

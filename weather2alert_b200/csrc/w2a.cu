@@ -465,6 +465,29 @@ int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward
   return W2A_OK;
 }
 
+namespace {
+int launch_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, w2a::RolloutArgs& a, void* state, double* ep_return,
+                   double* stats, bool policy) {
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  a.tb = ctx->tb;
+  a.st_static = plane_static(state);
+  a.st_mut = plane_mut(state, n);
+  a.ep_return = ep_return;
+  a.stats = stats;
+  a.n = static_cast<int>(n);
+  a.steps = steps;
+  int grid = 0;
+  int rc = policy ? grid_for(ctx, w2a::rollout_kernel<true>, 128, 0, 16, n, &grid)
+                  : grid_for(ctx, w2a::rollout_kernel<false>, 128, 0, 16, n, &grid);  // 4 warps x 4 envs per CTA pass
+  if (rc) return rc;
+  if (policy) w2a::rollout_kernel<true><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else w2a::rollout_kernel<false><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  ctx->launches++;
+  W2A_CUDA(ctx, cudaGetLastError());
+  return W2A_OK;
+}
+}  // namespace
+
 int w2a_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, const uint8_t* actions, uint64_t seed, float p_alert,
                 void* state, double* ep_return, double* stats) {
   int rc = check_ready(ctx, "w2a_rollout", n);
@@ -473,26 +496,26 @@ int w2a_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, const uint8_t*
   if (!state || !ep_return || steps < 0) return fail(ctx, W2A_E_INVALID, "w2a_rollout: bad argument");
   if (!actions && !(p_alert >= 0.f && p_alert <= 1.f))
     return fail(ctx, W2A_E_INVALID, "w2a_rollout: p_alert=%g not in [0,1]", static_cast<double>(p_alert));
-  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
-  w2a::RolloutArgs a;
-  a.tb = ctx->tb;
-  a.st_static = plane_static(state);
-  a.st_mut = plane_mut(state, n);
+  w2a::RolloutArgs a{};
   a.actions = actions;
   a.seed = seed;
   const double thr = static_cast<double>(p_alert) * 4294967296.0;
   a.threshold = thr >= 4294967295.0 ? 0xffffffffu : static_cast<unsigned>(thr);
-  a.ep_return = ep_return;
-  a.stats = stats;
-  a.n = static_cast<int>(n);
-  a.steps = steps;
-  int grid = 0;
-  rc = grid_for(ctx, w2a::rollout_kernel, 128, 0, 16, n, &grid);  // 4 warps x 4 envs per CTA pass
+  return launch_rollout(ctx, stream, n, steps, a, state, ep_return, stats, false);
+}
+
+int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const double* policy, int stochastic,
+                       uint64_t seed, void* state, double* ep_return, double* stats) {
+  int rc = check_ready(ctx, "w2a_rollout_policy", n);
   if (rc) return rc;
-  w2a::rollout_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  ctx->launches++;
-  W2A_CUDA(ctx, cudaGetLastError());
-  return W2A_OK;
+  if (n == 0 || steps == 0) return W2A_OK;
+  if (!state || !ep_return || !policy || steps < 0)
+    return fail(ctx, W2A_E_INVALID, "w2a_rollout_policy: bad argument");
+  w2a::RolloutArgs a{};
+  a.policy = policy;
+  a.stochastic = stochastic != 0;
+  a.seed = seed;
+  return launch_rollout(ctx, stream, n, steps, a, state, ep_return, stats, true);
 }
 
 int64_t w2a_launch_count(const w2a_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -911,7 +911,12 @@ struct RolloutArgs {
   double* ep_return;       // [n], +=
   double* stats;           // [kNumStats], += (see StatIndex)
   int n, steps;
+  // closed-loop logistic policy (rollout_kernel<true>): kPolicyLen float64 = one weight per observation
+  // slot (info["feature_names"] order; slot 27, the significance label, is ignored) and the bias
+  const double* policy;
+  int stochastic;          // 0: action = logit > 0; 1: action = hash(seed, env, step) < sigmoid(logit) * 2^32
 };
+constexpr int kPolicyLen = kObsDim + 1;
 
 // One butterfly level of the transposing reduction: lanes whose bit is set keep the upper
 // half of the values and send the lower half, and vice versa; after levels 4, 2, 1 lane q of
@@ -943,7 +948,12 @@ enum StatIndex {
   kStA50Sum, kStA80Sum, kStA100Sum, kStACount
 };
 
-__global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
+// POLICY = false: open-loop actions (bank or Bernoulli hash).  POLICY = true: the action of day d is
+// drawn by a logistic policy from the observation the agent holds before acting on day d -- the row of
+// day d-1 (day 0 on days 0 and 1: the observation lags a day, quirk Q1) with the agent slots as the
+// step of day d-1 returned them; only envs at the start of a summer (t = 0) take part.
+template <bool POLICY>
+__global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const RolloutArgs p) {
   __shared__ double s_stats[kNumStats];
   __shared__ unsigned char s_days[4][4][24];  // [warp][group][chunk]: issued-alert bits of the episode so far
   if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0.0;
@@ -984,6 +994,26 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
     const double c_lag_b = o0.x, c_lag_e = o0.y, c_str_b = o0.z, c_str_e = o0.w;
     const double c_rem_b = o1.x, c_rem_e = o1.y, c_bias_b = o1.z, c_bias_e = o1.w;
 
+    // ---- closed-loop policy: this lane's four table weights, the agent weights, what the agent last saw ----
+    double th_a0 = 0.0, th_a1 = 0.0, th_b0 = 0.0, th_b1 = 0.0, th_lag = 0.0, th_streak = 0.0, th_rem = 0.0,
+           th_2wks = 0.0, th_bias = 0.0;
+    double pt_prev = 0.0;                  // policy's table logit of the row the agent saw last
+    int lag_seen = 0, streak_seen = 0, cnt_seen = 0;  // agent slots of that observation (remaining budget = rem)
+    if (POLICY) {
+      // record position -> observation slot: 0..22 -> same, 23 -> 26 (issued_in_advance), 24..31 -> none
+      const int pb0 = 16 + 2 * q, pb1 = 17 + 2 * q;
+      th_a0 = __ldg(p.policy + 2 * q);
+      th_a1 = __ldg(p.policy + 2 * q + 1);
+      th_b0 = pb0 < 24 ? __ldg(p.policy + slot_of_feature(pb0)) : 0.0;
+      th_b1 = pb1 < 24 ? __ldg(p.policy + slot_of_feature(pb1)) : 0.0;
+      th_lag = __ldg(p.policy + 23);
+      th_streak = __ldg(p.policy + 24);
+      th_rem = __ldg(p.policy + 25);
+      th_2wks = __ldg(p.policy + 28);
+      th_bias = __ldg(p.policy + kObsDim);
+      if (t != 0) done = true;  // mid-summer envs are left alone: their last observation is not in the state
+    }
+
     double ret = 0.0;
     int k = 0;  // steps taken by this env in this call
     // the 4 envs of a warp may need different numbers of chunks: loop while any is alive
@@ -992,7 +1022,7 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
       // days this env executes in this chunk: t .. t+nv-1, the last one possibly terminal
       const int nv = live ? min(8, min(p.steps - k, n_days - t)) : 0;
       // ---- table part of the logits of the chunk's days ----------------------------------
-      double pbv[8], pev[8];
+      double pbv[8], pev[8], ptv[POLICY ? 8 : 1];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const unsigned row = row0 + static_cast<unsigned>(min(t + j, n_days - 1));
@@ -1000,17 +1030,18 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
         const double2 xa = __ldg(xr), xb = __ldg(xr + 8);
         pbv[j] = fma(xa.x, wab0, xa.y * wab1) + fma(xb.x, wbb0, xb.y * wbb1);
         pev[j] = fma(xa.x, wae0, xa.y * wae1) + fma(xb.x, wbe0, xb.y * wbe1);
+        if (POLICY) ptv[j] = fma(xa.x, th_a0, xa.y * th_a1) + fma(xb.x, th_b0, xb.y * th_b1);
       }
-      // ---- this chunk's 8 action bits: lane q fetches day q's ------------------------------
-      int a_mine = 0;
-      if (q < nv) {
-        if (p.actions) a_mine = __ldg(p.actions + static_cast<size_t>(k + q) * p.n + e) != 0;
-        else a_mine = rollout_hash(p.seed, static_cast<unsigned>(e), static_cast<unsigned>(k + q)) < p.threshold;
-      }
-      const unsigned am = (__ballot_sync(kFull, a_mine) >> (8 * g)) & 0xffu;
-      // ---- integer recurrence of the chunk (env.py:242-250), replayed by every lane -----------
       unsigned actm = 0, refm = 0;
-      {
+      if (!POLICY) {
+        // ---- this chunk's 8 action bits: lane q fetches day q's ------------------------------
+        int a_mine = 0;
+        if (q < nv) {
+          if (p.actions) a_mine = __ldg(p.actions + static_cast<size_t>(k + q) * p.n + e) != 0;
+          else a_mine = rollout_hash(p.seed, static_cast<unsigned>(e), static_cast<unsigned>(k + q)) < p.threshold;
+        }
+        const unsigned am = (__ballot_sync(kFull, a_mine) >> (8 * g)) & 0xffu;
+        // ---- integer recurrence of the chunk (env.py:242-250), replayed by every lane -----------
         int r = rem;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -1021,6 +1052,54 @@ __global__ void __launch_bounds__(128, 4) rollout_kernel(const RolloutArgs p) {
           actm |= act << j;
           refm |= (a & atb) << j;
         }
+      } else {
+        // ---- the policy's table logits of the chunk's rows, one per lane, then known to every lane ----
+        double t8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t8[j] = ptv[j];
+        fold_level<8>(t8, (q & 4) != 0, 4);
+        double t4[4] = {t8[0], t8[1], t8[2], t8[3]};
+        fold_level<4>(t4, (q & 2) != 0, 2);
+        double t2[2] = {t4[0], t4[1]};
+        fold_level<2>(t2, (q & 1) != 0, 1);
+        double ptall[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ptall[j] = __shfl_sync(kFull, t2[0], (lane & 24) + j);
+        if (t == 0) pt_prev = ptall[0];  // the reset observation shows day 0
+        // ---- decisions and integer recurrence, day after day (every lane replays them) ----------------
+        int r = rem, s_cur = streak;
+        unsigned w14 = win;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          double logit = (j == 0 ? pt_prev : ptall[j - 1]) + th_bias;
+          logit = fma(static_cast<double>(lag_seen), th_lag, logit);
+          logit = fma(static_cast<double>(streak_seen), th_streak, logit);
+          logit = fma(static_cast<double>(r), th_rem, logit);
+          logit = fma(static_cast<double>(cnt_seen), th_2wks, logit);
+          unsigned a;
+          if (p.stochastic) {
+            const double thr = expit(logit) * 4294967296.0;
+            const unsigned thr_u = thr >= 4294967295.0 ? 0xffffffffu : static_cast<unsigned>(thr);
+            a = rollout_hash(p.seed, static_cast<unsigned>(e), static_cast<unsigned>(k + j)) < thr_u ? 1u : 0u;
+          } else {
+            a = logit > 0.0 ? 1u : 0u;
+          }
+          if (j < nv) {
+            const unsigned atb = (r == 0) ? 1u : 0u;
+            const unsigned act = a & ~atb;
+            r -= static_cast<int>(act);
+            actm |= act << j;
+            refm |= (a & atb) << j;
+            // what the step of this day hands back (env.py:190-193): lag (0 on day 0), the streak before
+            // today's action, the 14-day count with it
+            lag_seen = (t + j) > 0 ? static_cast<int>(act) : 0;
+            streak_seen = s_cur;
+            s_cur = act ? s_cur + 1 : 0;
+            w14 = ((w14 << 1) | act) & 0x3fffu;
+            cnt_seen = __popc(w14);
+          }
+        }
+        pt_prev = ptall[7];
       }
       // ---- transpose: lane q gets the table logits of day q ---------------------------------
       fold_level<8>(pbv, (q & 4) != 0, 4);

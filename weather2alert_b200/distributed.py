@@ -84,10 +84,10 @@ def summarize(stats: torch.Tensor) -> dict:
     return out
 
 
-def rollout_action_bits(seed: int, envs, steps, p_alert: float):
-    """The counter-based action stream of `w2a_rollout(actions=NULL)` on the host:
-    ``bits[k, i] = hash(seed, envs[i], steps[k]) < p_alert * 2**32`` (splitmix64 finaliser; same
-    arithmetic as `rollout_hash` in csrc/w2a_kernels.cuh).  Returns bool [len(steps), len(envs)]."""
+def rollout_hash(seed: int, envs, steps):
+    """The counter-based 32-bit stream of the rollout kernels on the host: ``u[k, i] = hash(seed, envs[i],
+    steps[k])`` (splitmix64 finaliser; same arithmetic as `rollout_hash` in csrc/w2a_kernels.cuh).
+    Returns uint64 [len(steps), len(envs)] holding values below 2**32."""
     import numpy as np
 
     e = np.asarray(envs, dtype=np.uint64)[None, :]
@@ -97,6 +97,18 @@ def rollout_action_bits(seed: int, envs, steps, p_alert: float):
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z = z ^ (z >> np.uint64(31))
-    thr = p_alert * 4294967296.0
-    thr = 0xFFFFFFFF if thr >= 4294967295.0 else int(thr)
-    return (z >> np.uint64(32)) < np.uint64(thr)
+    return z >> np.uint64(32)
+
+
+def rollout_threshold(p):
+    """Probability -> the 32-bit threshold the kernels compare the hash with (`p * 2**32`, saturated)."""
+    import numpy as np
+
+    thr = np.asarray(p, dtype=np.float64) * 4294967296.0
+    return np.where(thr >= 4294967295.0, 4294967295.0, thr).astype(np.uint64)
+
+
+def rollout_action_bits(seed: int, envs, steps, p_alert: float):
+    """The action stream of `w2a_rollout(actions=NULL)` on the host: ``bits[k, i] = rollout_hash(seed,
+    envs[i], steps[k]) < p_alert * 2**32``.  Returns bool [len(steps), len(envs)]."""
+    return rollout_hash(seed, envs, steps) < rollout_threshold(p_alert)

@@ -308,14 +308,20 @@ class HeatAlertVectorEnv:
 
     # ---- episode-fused rollout ------------------------------------------------------------------
     def rollout(self, steps: int | None = None, actions: torch.Tensor | None = None, p_alert: float = 0.5,
-                seed: int = 0, stats: torch.Tensor | None = None):
+                seed: int = 0, stats: torch.Tensor | None = None, policy=None, stochastic: bool = False):
         """Run up to `steps` steps (default: to the end of the summer) of every env in ONE kernel
         launch -- the `while not done: step(a)` loop of `env.py:273-276` without materialising
         observations.  `actions` is a ``uint8/bool [steps, N]`` CUDA tensor, or None for
         counter-based Bernoulli(`p_alert`) actions (`rollout_action_bits` reproduces them).
         Returns ``(episode_return float64[N], stats float64[6])``; `stats` (see
         `distributed.STAT_NAMES`) is accumulated into, so it can be carried across calls and
-        all-reduced with `distributed.reduce_stats`.  Envs that finish are NOT auto-reset."""
+        all-reduced with `distributed.reduce_stats`.  Envs that finish are NOT auto-reset.
+
+        `policy` (30 numbers: one weight per observation slot in `feature_names` order -- slot 27, the
+        significance label, is ignored -- and the bias) puts the agent inside the launch instead:
+        ``a = [sum_s policy[s] * obs[s] + policy[29] > 0]``, or with ``stochastic=True`` a Bernoulli draw
+        with probability ``sigmoid(logit)`` from the counter-based stream of `seed`.  It needs envs at the
+        start of a summer (right after `reset()`); others are left untouched."""
         if self._next_term is None:
             raise RuntimeError("call reset() before rollout()")
         if steps is None:
@@ -329,6 +335,15 @@ class HeatAlertVectorEnv:
         if stats is None:
             stats = torch.zeros(15, dtype=torch.float64, device=self.device)
         ep_return = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        if policy is not None:
+            if actions is not None:
+                raise ValueError("rollout: give either `actions` or `policy`")
+            theta = torch.as_tensor(policy, dtype=torch.float64).reshape(-1).to(self.device).contiguous()
+            if theta.numel() != _lib.POLICY_LEN:
+                raise ValueError(f"policy must hold {_lib.POLICY_LEN} numbers (29 observation slots + bias)")
+            self.core.rollout_policy(self._state, steps, ep_return, theta, stochastic=stochastic, seed=seed, stats=stats)
+            self._step_no += steps
+            return ep_return, stats
         self.core.rollout(self._state, steps, ep_return, actions=actions, seed=seed, p_alert=p_alert, stats=stats)
         self._step_no += steps
         return ep_return, stats
