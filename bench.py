@@ -323,6 +323,32 @@ def run_ours(args):
                     "mean_return": ro_sum["mean_return"],
                     "same_returns_as_stepping": bool(abs(ro_sum["mean_return"] - stats["mean_return"]) <= 1e-6 * abs(stats["mean_return"]))}
 
+    # the agent inside the launch: a logistic policy on the observation (w2a_rollout_policy), deterministic and
+    # stochastic, same summer; timed like the open-loop rollout
+    theta = torch.zeros(30, dtype=torch.float64)
+    theta[0], theta[6], theta[25], theta[28], theta[29] = 2.0, 0.004, 0.05, -0.3, -2.2  # heat_qi, dos, budget left, alerts in 2 weeks
+    theta = theta.to(dev)
+    for mode, stochastic in (("policy_deterministic", False), ("policy_stochastic", True)):
+        pms = []
+        for _ in range(3):
+            do_reset()
+            ep_ret.zero_()
+            ro_stats.zero_()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            r0.record()
+            core.rollout_policy(state, T, ep_ret, theta, stochastic=stochastic, seed=99, stats=ro_stats)
+            r1.record()
+            torch.cuda.synchronize()
+            pms.append(r0.elapsed_time(r1))
+        p_t = torch.tensor([min(pms[1:])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(p_t, op=dist.ReduceOp.MAX)
+        p_sum = summarize(reduce_stats(ro_stats))
+        rollout_info[mode] = {"value": n * world * T / (float(p_t.item()) * 1e-3), "ms_per_rollout": float(p_t.item()),
+                              "mean_return": p_sum["mean_return"], "alert_freq": p_sum.get("alert_freq"),
+                              "kernel": "rollout_kernel<POLICY> (logistic policy on the 29-slot observation, in the launch)"}
+
     # ---- policy in the loop (BASELINE configs[4] style): a small torch MLP policy on the observations and
     # the step kernel, a whole summer + reset captured in ONE CUDA graph (HeatAlertVectorEnv.graphed_rollout)
     policy_info = None
