@@ -145,6 +145,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.w2a_destroy(None) == 0
 
 
+def test_auto_variant_rule_above_the_abi():
+    """TABLE only for big batches of envs on their own county's coefficients (the C library's AUTO never picks it)."""
+    from weather2alert_b200 import _lib
+    from weather2alert_b200.core import HeatAlertCore
+
+    pick = lambda n, canonical: HeatAlertCore.choose_variant(HeatAlertCore, n, canonical)  # noqa: E731 - no GPU needed
+    assert pick(1 << 20, True) == _lib.STEP_TABLE and pick(1 << 23, True) == _lib.STEP_TABLE
+    assert pick(1 << 20, False) == _lib.STEP_AUTO  # similar-county augmentation
+    assert pick(4096, True) == _lib.STEP_AUTO and pick(HeatAlertCore.TABLE_MIN_ENVS - 1, True) == _lib.STEP_AUTO
+    assert _lib.POLICY_LEN == 30 and _lib.STEP_TABLE == 3
+
+
 def test_no_product_module_imports_the_oracle():
     pkg = os.path.join(REPO, "weather2alert_b200")
     for root, _, files in os.walk(pkg):
