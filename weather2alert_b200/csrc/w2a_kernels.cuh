@@ -676,8 +676,11 @@ struct __align__(128) TableScratchWarp {
 constexpr int kTableWarps = 8;
 constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScratchWarp));
 
+#ifndef W2A_TABLE_ROWS
+#define W2A_TABLE_ROWS 2  // rounds of observation-row gathers in flight per warp (B200 sweep: 2 with 4 CTAs/SM >= 8 with 3)
+#endif
 #ifndef W2A_TABLE_MINBLOCKS
-#define W2A_TABLE_MINBLOCKS 3
+#define W2A_TABLE_MINBLOCKS 4
 #endif
 
 template <int ADT>
@@ -732,13 +735,31 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     const float4 o0 = ldg_keep(zrec, keep);
     const float2 o1 = __ldg(reinterpret_cast<const float2*>(zrec + 1));
     const double2 z = __ldg(reinterpret_cast<const double2*>(zrec + 2) + (fast ? yr - zl * kZPerLine : 0u));
-    float4 rows[8];  // observation rows: 8 lanes copy one float32 row, four neighbouring envs per round
+    float4 rows[W2A_TABLE_ROWS];  // observation rows: 8 lanes copy one float32 row, four neighbouring envs per round
+    auto load_rows = [&](int first) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int j = 4 * it + g;
-      const unsigned syj = __shfl_sync(kFull, sy, j);
-      rows[it] = __ldg(xobs_lane + static_cast<size_t>(((fast_mask >> j) & 1u) ? syj : 0u) * 8);
-    }
+      for (int it = 0; it < W2A_TABLE_ROWS; ++it) {
+        const int j = 4 * (first + it) + g;
+        const unsigned syj = __shfl_sync(kFull, sy, j);
+        rows[it] = __ldg(xobs_lane + static_cast<size_t>(((fast_mask >> j) & 1u) ? syj : 0u) * 8);
+      }
+    };
+    auto stage_rows = [&](int first) {
+#pragma unroll
+      for (int it = 0; it < W2A_TABLE_ROWS; ++it) {
+        const int j = 4 * (first + it) + g;
+        if ((fast_mask >> j) & 1u) {
+          float* st = stage + j * kObsDim + 4 * q;
+          st[0] = rows[it].x;
+          if (q < 7) {
+            st[1] = rows[it].y;
+            st[2] = rows[it].z;
+            st[3] = rows[it].w;
+          }
+        }
+      }
+    };
+    load_rows(0);
     if (valid) st_stream(p.st_mut + e, mv);
     if (wg + warps_total < n_groups) fetch(wg + warps_total);
     const bool write_obs = valid && !tr.done;
@@ -787,17 +808,9 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     }
     __syncwarp();
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int j = 4 * it + g;
-      if ((fast_mask >> j) & 1u) {
-        float* st = stage + j * kObsDim + 4 * q;
-        st[0] = rows[it].x;
-        if (q < 7) {
-          st[1] = rows[it].y;
-          st[2] = rows[it].z;
-          st[3] = rows[it].w;
-        }
-      }
+    for (int first = 0; first < 8; first += W2A_TABLE_ROWS) {
+      if (first > 0) load_rows(first);
+      stage_rows(first);
     }
     __syncwarp();
     my_row[23] = static_cast<float>(tr.lag);
