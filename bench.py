@@ -198,7 +198,7 @@ def run_ours(args):
         variant = core.choose_variant(n, canonical=not wl["augment"])
     kernel_name = {_lib.STEP_TABLE: "logit_table_kernel + step_table_kernel", _lib.STEP_COOP: "step_coop_kernel",
                    _lib.STEP_THREAD: "step_thread_kernel"}.get(
-        variant, "step_coop_kernel" if n >= 2048 else "step_thread_kernel")
+        variant, "step_coop_kernel")
 
     state = core.alloc_state(n)
     obs = torch.zeros((n, 29), dtype=torch.float32, device=dev)

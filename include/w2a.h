@@ -50,9 +50,10 @@ extern "C" {
 #define W2A_ACT_I64 2
 
 /* kernel variant for w2a_step */
-#define W2A_STEP_AUTO 0   /* THREAD below 2048 envs, COOP from there on */
-#define W2A_STEP_THREAD 1 /* one thread per env (small batches, reference kernel) */
-#define W2A_STEP_COOP 2   /* 8 lanes per env: whole-line gathers, float64 fold in shared memory, TMA obs store */
+#define W2A_STEP_AUTO 0   /* = COOP (it is the faster of the two at every batch size, a single env included) */
+#define W2A_STEP_THREAD 1 /* one thread per env: the straightforward kernel, kept as the in-tree cross-check */
+#define W2A_STEP_COOP 2   /* 8 lanes per env: whole-line gathers, float64 fold in shared memory, TMA obs store;
+                             small batches spread their warps over the SMs with every gather in flight at once */
 #define W2A_STEP_TABLE 3  /* two launches: today's logits of every (county, sample, year) once (a float64 GEMM per
                              county on the FP64 tensor path), then one 128-byte record + one observation row per
                              env; for big non-augmented env sets in lock step; needs w2a_set_county_map; envs the

@@ -19,7 +19,6 @@ namespace {
 
 // below this the thread-per-env kernel is used by W2A_STEP_AUTO (B200: at 4 096 envs the
 // cooperative kernel already takes 5.2 us per step against 9.6 us, profiles/r01)
-constexpr int64_t kCoopMinEnvs = 2048;
 constexpr int kHostStreams = 3;
 constexpr int64_t kHostChunk = 1 << 16;  // envs per pipelined chunk of the *_host calls
 
@@ -124,7 +123,18 @@ int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int varia
     constexpr int kBlock = 32 * w2a::kCoopWarps;
     int rc = grid_for(ctx, w2a::step_coop_kernel<ADT>, kBlock, w2a::kCoopSmemBytes, kBlock, a.n, &grid);
     if (rc) return rc;
-    w2a::step_coop_kernel<ADT><<<grid, kBlock, w2a::kCoopSmemBytes, st>>>(a);
+    // small batches (launch-latency bound): spread the warps over the SMs instead of packing 8 per CTA
+    const int64_t groups = (static_cast<int64_t>(a.n) + 31) / 32;
+    const int warps = static_cast<int>(std::min<int64_t>(w2a::kCoopWarps, std::max<int64_t>(1, groups / ctx->sm_count)));
+    if (warps <= 2) {  // at most two groups per SM: every round of a group in flight at once, one or two warps per CTA
+      int unused = 0;  // (sets the instance's shared-memory attribute once)
+      rc = grid_for(ctx, w2a::step_coop_kernel<ADT, 7>, kBlock, w2a::kCoopSmemBytes, kBlock, a.n, &unused);
+      if (rc) return rc;
+      const int small_grid = static_cast<int>((groups + warps - 1) / warps);
+      w2a::step_coop_kernel<ADT, 7><<<small_grid, 32 * warps, warps * sizeof(w2a::WarpScratch), st>>>(a);
+    } else {
+      w2a::step_coop_kernel<ADT><<<grid, kBlock, w2a::kCoopSmemBytes, st>>>(a);
+    }
   }
   ctx->launches++;
   W2A_CUDA(ctx, cudaGetLastError());
@@ -134,7 +144,7 @@ int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int varia
 int step_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const void* action, int action_dtype,
                 const uint2* st_static, uint2* st_mut, float* obs, float* reward,
                 uint8_t* terminated, int32_t* remaining, uint8_t* at_budget, int variant) {
-  if (variant == W2A_STEP_AUTO) variant = n < kCoopMinEnvs ? W2A_STEP_THREAD : W2A_STEP_COOP;
+  if (variant == W2A_STEP_AUTO) variant = W2A_STEP_COOP;  // faster than THREAD at every batch size, n = 1 included
   if (variant != W2A_STEP_THREAD && variant != W2A_STEP_COOP && variant != W2A_STEP_TABLE)
     return fail(ctx, W2A_E_INVALID, "w2a_step: unknown variant %d", variant);
   if (variant == W2A_STEP_TABLE && !ctx->tb.z_tab)
@@ -440,7 +450,7 @@ int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward
   uint2* sstat = plane_static(h->state);
   uint2* smut = plane_mut(h->state, n);
   // one kernel variant for the whole batch, so that chunking never changes a result bit
-  const int variant = n < kCoopMinEnvs ? W2A_STEP_THREAD : W2A_STEP_COOP;
+  const int variant = W2A_STEP_COOP;
   int ci = 0;
   for (int64_t c0 = 0; c0 < n; c0 += kHostChunk, ++ci) {
     const int64_t m = std::min(kHostChunk, n - c0);

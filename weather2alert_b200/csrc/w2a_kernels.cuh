@@ -354,8 +354,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 //            staged observation row; the warp's 32 rows (3712 contiguous bytes) then leave
 //            through one bulk (TMA) store.
 // =========================================================================================
-template <int ADT>
-__global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop_kernel(const StepArgs p) {
+// AHEAD = rounds of table loads in flight ahead of the one being consumed: kAhead for big batches (two CTAs
+// per SM hide the rest), 7 = the whole group at once for small, launch-latency-bound batches.
+template <int ADT, int AHEAD = kAhead>
+__global__ void __launch_bounds__(32 * kCoopWarps, AHEAD > 4 ? 1 : W2A_COOP_MINBLOCKS) step_coop_kernel(const StepArgs p) {
+  constexpr int PRE = kPre < AHEAD ? kPre : AHEAD;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
@@ -393,10 +396,10 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
 
   // Software pipeline over the warp's groups of 32 envs: while group G is in phase C (fold,
   // sigmoids, stores), the state transition of group G+1 is already done and its first
-  // kAhead rounds of table loads are in flight; the per-env inputs of group G+2 are being
+  // AHEAD rounds of table loads are in flight; the per-env inputs of group G+2 are being
   // fetched.  `cur_*` belong to G, `nxt_*` to G+1, `in_*` are raw inputs one step further.
   int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  RoundLoads ring[kAhead + 1];
+  RoundLoads ring[AHEAD + 1];
   uint2 in_sv = make_uint2(0u, 0u), in_mv = make_uint2(0u, 0u);
   int in_a = 0;
   auto fetch_inputs = [&](int group) {
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
   };
   Transition cur_tr = {};
   unsigned cur_cv = 0u;
-  // phase A of `group` from the fetched inputs + its first kAhead rounds of loads
+  // phase A of `group` from the fetched inputs + its first AHEAD rounds of loads
   auto open_group = [&](int group) {
     if (group < n_groups) {
       const uint2 sv = in_sv;
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
       if (e < p.n) st_stream(p.st_mut + e, mv);
       cur_cv = sv.y;
 #pragma unroll
-      for (int d = 0; d < kPre; ++d) {
+      for (int d = 0; d < PRE; ++d) {
         const unsigned rowd = __shfl_sync(kFull, cur_tr.row, 2 * d + row_g);
         const unsigned cvd = __shfl_sync(kFull, cur_cv, 2 * d + row_g);
         ring[d] = issue_round(x_lane, w_lane, rowd, cvd, keep);
@@ -447,22 +450,22 @@ __global__ void __launch_bounds__(32 * kCoopWarps, W2A_COOP_MINBLOCKS) step_coop
     }
 
     // ---- phase B ---------------------------------------------------------------------------
-    // kAhead rounds of loads are in flight while a round is being consumed; the first kPre of
+    // AHEAD rounds of loads are in flight while a round is being consumed; the first PRE of
     // them were issued one group earlier (open_group), the others follow now
 #pragma unroll
-    for (int d = kPre; d < kAhead; ++d) {
+    for (int d = PRE; d < AHEAD; ++d) {
       const unsigned rowd = __shfl_sync(kFull, tr.row, 2 * d + row_g);
       const unsigned cvd = __shfl_sync(kFull, cv, 2 * d + row_g);
       ring[d] = issue_round(x_lane, w_lane, rowd, cvd, keep);
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      if (it + kAhead < 8) {
-        const unsigned rowd = __shfl_sync(kFull, tr.row, 2 * (it + kAhead) + row_g);
-        const unsigned cvd = __shfl_sync(kFull, cv, 2 * (it + kAhead) + row_g);
-        ring[(it + kAhead) % (kAhead + 1)] = issue_round(x_lane, w_lane, rowd, cvd, keep);
+      if (it + AHEAD < 8) {
+        const unsigned rowd = __shfl_sync(kFull, tr.row, 2 * (it + AHEAD) + row_g);
+        const unsigned cvd = __shfl_sync(kFull, cv, 2 * (it + AHEAD) + row_g);
+        ring[(it + AHEAD) % (AHEAD + 1)] = issue_round(x_lane, w_lane, rowd, cvd, keep);
       }
-      const RoundLoads& cur = ring[it % (kAhead + 1)];
+      const RoundLoads& cur = ring[it % (AHEAD + 1)];
       const double pb = fma(cur.xa.x, static_cast<double>(cur.wa.x), cur.xa.y * static_cast<double>(cur.wa.z)) +
                         fma(cur.xb.x, static_cast<double>(cur.wb.x), cur.xb.y * static_cast<double>(cur.wb.z));
       const double pe = fma(cur.xa.x, static_cast<double>(cur.wa.y), cur.xa.y * static_cast<double>(cur.wa.w)) +
