@@ -173,7 +173,9 @@ int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const d
 /* ---- host-buffer entry points: the call a CPU-side RL loop makes ------------------
  * The context owns a device-resident env set; every call copies its inputs from and its
  * outputs to HOST memory (pinned for full PCIe speed), pipelined in chunks over several
- * streams, and returns after the outputs have landed. */
+ * streams, and returns after the outputs have landed.  Env sets of at most 1024 envs move their
+ * actions and all step outputs through one pinned staging block (one copy each way), so the caller's
+ * arrays may be ordinary pageable memory at no cost. */
 int w2a_host_envs_create(w2a_ctx* ctx, int64_t n);
 int w2a_host_envs_destroy(w2a_ctx* ctx);
 int w2a_reset_host(w2a_ctx* ctx, const int32_t* loc, const int32_t* year,

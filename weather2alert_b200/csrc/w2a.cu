@@ -34,7 +34,16 @@ struct HostEnvs {
   int32_t* idx = nullptr;  // 5 planes of n int32: loc, year, coef_col, coef_idx, budget
   uint8_t* mask = nullptr;
   cudaStream_t streams[kHostStreams] = {};
+  // small batches (n <= kHostPackedMax): the step outputs are one device block [obs | reward | remaining |
+  // terminated | at_budget] that comes back with ONE copy into a pinned staging block (and the actions go
+  // out through it), whatever kind of host memory the caller's arrays are -- the per-call cost of a
+  // single env is a handful of driver calls instead of six copies and three synchronisations
+  bool packed = false;
+  unsigned char* pack_dev = nullptr;
+  unsigned char* pack_host = nullptr;  // pinned: [outputs as on the device | actions]
+  size_t pack_bytes = 0;
 };
+constexpr int64_t kHostPackedMax = 1024;
 
 char g_create_error[512] = "";
 constexpr int kMaxKernels = 16;
@@ -358,11 +367,16 @@ int w2a_host_envs_destroy(w2a_ctx* ctx) {
   cudaDeviceSynchronize();
   cudaFree(h->state);
   cudaFree(h->action);
-  cudaFree(h->obs);
-  cudaFree(h->reward);
-  cudaFree(h->terminated);
-  cudaFree(h->remaining);
-  cudaFree(h->at_budget);
+  if (h->packed) {
+    cudaFree(h->pack_dev);
+    cudaFreeHost(h->pack_host);
+  } else {
+    cudaFree(h->obs);
+    cudaFree(h->reward);
+    cudaFree(h->terminated);
+    cudaFree(h->remaining);
+    cudaFree(h->at_budget);
+  }
   cudaFree(h->idx);
   cudaFree(h->mask);
   for (auto& s : h->streams)
@@ -385,11 +399,24 @@ int w2a_host_envs_create(w2a_ctx* ctx, int64_t n) {
   const size_t un = static_cast<size_t>(n);
   W2A_CUDA(ctx, cudaMalloc(&h->state, w2a_state_bytes(n)));
   W2A_CUDA(ctx, cudaMalloc(&h->action, un));
-  W2A_CUDA(ctx, cudaMalloc(&h->obs, un * W2A_OBS_DIM * sizeof(float)));
-  W2A_CUDA(ctx, cudaMalloc(&h->reward, un * sizeof(float)));
-  W2A_CUDA(ctx, cudaMalloc(&h->terminated, un));
-  W2A_CUDA(ctx, cudaMalloc(&h->remaining, un * sizeof(int32_t)));
-  W2A_CUDA(ctx, cudaMalloc(&h->at_budget, un));
+  h->packed = n <= kHostPackedMax;
+  if (h->packed) {
+    const size_t obs_b = un * W2A_OBS_DIM * sizeof(float);
+    h->pack_bytes = obs_b + un * 4 + un * 4 + un + un;
+    W2A_CUDA(ctx, cudaMalloc(&h->pack_dev, h->pack_bytes));
+    W2A_CUDA(ctx, cudaMallocHost(&h->pack_host, h->pack_bytes + un));
+    h->obs = reinterpret_cast<float*>(h->pack_dev);
+    h->reward = reinterpret_cast<float*>(h->pack_dev + obs_b);
+    h->remaining = reinterpret_cast<int32_t*>(h->pack_dev + obs_b + un * 4);
+    h->terminated = h->pack_dev + obs_b + un * 8;
+    h->at_budget = h->pack_dev + obs_b + un * 9;
+  } else {
+    W2A_CUDA(ctx, cudaMalloc(&h->obs, un * W2A_OBS_DIM * sizeof(float)));
+    W2A_CUDA(ctx, cudaMalloc(&h->reward, un * sizeof(float)));
+    W2A_CUDA(ctx, cudaMalloc(&h->terminated, un));
+    W2A_CUDA(ctx, cudaMalloc(&h->remaining, un * sizeof(int32_t)));
+    W2A_CUDA(ctx, cudaMalloc(&h->at_budget, un));
+  }
   W2A_CUDA(ctx, cudaMalloc(&h->idx, un * 5 * sizeof(int32_t)));
   W2A_CUDA(ctx, cudaMalloc(&h->mask, un));
   W2A_CUDA(ctx, cudaMemset(h->obs, 0, un * W2A_OBS_DIM * sizeof(float)));
@@ -451,6 +478,24 @@ int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward
   uint2* smut = plane_mut(h->state, n);
   // one kernel variant for the whole batch, so that chunking never changes a result bit
   const int variant = W2A_STEP_COOP;
+  if (h->packed) {
+    const size_t un = static_cast<size_t>(n), obs_b = un * W2A_OBS_DIM * sizeof(float);
+    cudaStream_t st = h->streams[0];
+    unsigned char* stage_act = h->pack_host + h->pack_bytes;
+    std::memcpy(stage_act, action, un);
+    W2A_CUDA(ctx, cudaMemcpyAsync(h->action, stage_act, un, cudaMemcpyHostToDevice, st));
+    int rc = step_planes(ctx, st, n, h->action, W2A_ACT_U8, sstat, smut, h->obs, h->reward, h->terminated, h->remaining,
+                         h->at_budget, variant);
+    if (rc) return rc;
+    W2A_CUDA(ctx, cudaMemcpyAsync(h->pack_host, h->pack_dev, h->pack_bytes, cudaMemcpyDeviceToHost, st));
+    W2A_CUDA(ctx, cudaStreamSynchronize(st));
+    std::memcpy(obs, h->pack_host, obs_b);
+    std::memcpy(reward, h->pack_host + obs_b, un * 4);
+    if (remaining) std::memcpy(remaining, h->pack_host + obs_b + un * 4, un * 4);
+    std::memcpy(terminated, h->pack_host + obs_b + un * 8, un);
+    if (at_budget) std::memcpy(at_budget, h->pack_host + obs_b + un * 9, un);
+    return W2A_OK;
+  }
   int ci = 0;
   for (int64_t c0 = 0; c0 < n; c0 += kHostChunk, ++ci) {
     const int64_t m = std::min(kHostChunk, n - c0);
