@@ -299,3 +299,43 @@ def test_degenerate_table_shapes(S, Y, P, T):
         assert_obs_equal(obs.cpu().numpy(), o_ref, f"step {i}")
         np.testing.assert_allclose(reward.cpu().numpy(), r_ref, rtol=REWARD_RTOL, atol=REWARD_ATOL)
         np.testing.assert_array_equal(term.cpu().numpy().astype(bool), d_ref)
+
+
+@pytest.mark.parametrize("n_years,n_samples", [(18, 5), (9, 8), (25, 21)])
+def test_table_variant_shapes_off_the_beaten_path(n_years, n_samples):
+    """The TABLE variant's table build outside the real shapes: more than 16 years (its generic year-tile loop),
+    fewer / a non-multiple of 8 posterior samples, coefficient columns whose county is not in the feature store,
+    and the lock-step fast path itself (all envs canonical and on the same day) -- against the oracle."""
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200 import synthetic
+    from weather2alert_b200.core import HeatAlertCore
+
+    fips, zones = synthetic.synthetic_counties(12, seed=n_years)
+    years = list(range(2000, 2000 + n_years))
+    store = synthetic.make_store(fips, years, seed=3, zones=zones)
+    extra = [f for f in ("01001", "56045", "99999") if f not in fips]
+    fips_w = sorted(fips + extra)  # columns of counties the store does not hold: skipped by the table build
+    weights = synthetic.make_weights(fips_w, n_samples, seed=4)
+    core = HeatAlertCore(store, weights, "cuda:0")
+    assert (core.col_to_loc.cpu().numpy() < 0).sum() == len(extra)
+    n = 1500
+    rng = np.random.default_rng(11)
+    loc = rng.integers(0, len(fips), n).astype(np.int32)
+    col = np.array([fips_w.index(fips[i]) for i in loc], dtype=np.int32)  # canonical: the county's own column
+    idx = dict(loc=loc, year=rng.integers(0, n_years, n).astype(np.int32), coef_col=col,
+               coef_idx=rng.integers(0, n_samples, n).astype(np.int32), budget=rng.integers(0, 9, n).astype(np.int32))
+    state = core.alloc_state(n)
+    obs = torch.zeros((n, 29), device="cuda")
+    core.reset(state, obs, *(_dev(idx[k]) for k in ("loc", "year", "coef_col", "coef_idx")), budget=_dev(idx["budget"]))
+    assert bool((state.view(torch.int32).view(2, n, 2)[1, :, 1] < 0).all())  # every env carries the canonical bit
+    st, o_ref = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"], idx["coef_col"],
+                                idx["coef_idx"], idx["budget"])
+    reward = torch.zeros(n, device="cuda")
+    term = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    for i in range(40):
+        act = (rng.random(n) < 0.4).astype(np.int64)
+        core.step(state, _dev(act), obs, reward, term, variant=VARIANTS["table"])
+        o_ref, r_ref, d_ref, _, _ = orc.batch_step(store.feat, store.sig_code, weights.coef, st, act)
+        assert_obs_equal(obs.cpu().numpy(), o_ref, f"step {i}")
+        np.testing.assert_allclose(reward.cpu().numpy(), r_ref, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+        np.testing.assert_array_equal(term.cpu().numpy().astype(bool), d_ref)
