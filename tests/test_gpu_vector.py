@@ -260,3 +260,35 @@ def test_vector_env_auto_variant_picks_table(golden, monkeypatch):
         assert torch.equal(o1.view(torch.int32), o2.view(torch.int32)) and torch.equal(t1, t2), f"step {i}"
         assert torch.allclose(r1, r2, rtol=1e-6, atol=1e-10)
     assert (_lib.STEP_TABLE in {k[1] for k in small._bound}) and (_lib.STEP_COOP in {k[1] for k in forced._bound})
+
+
+def test_vector_env_intended_augmentation(golden, monkeypatch):
+    """`similar_climate_counties="intended"`: episodes move to a similar county (weather and column alike), stay
+    canonical (so the TABLE variant applies) and step like any other episode."""
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200 import HeatAlertVectorEnv, _lib
+    from weather2alert_b200.core import HeatAlertCore
+
+    store, weights = golden.store(), golden.weights("std")
+    monkeypatch.setattr(HeatAlertCore, "TABLE_MIN_ENVS", 1)
+    n = 500
+    env = HeatAlertVectorEnv(n, weights=weights, store=store, seed=21, autoreset=False)
+    obs, _ = env.reset(options={"similar_climate_counties": "intended"})
+    idx = {k: v.cpu().numpy() for k, v in env._idx.items()}
+    np.testing.assert_array_equal(idx["coef_col"], idx["list_idx"])
+    np.testing.assert_array_equal(idx["loc"], env.sampler.list_to_data[idx["list_idx"]])
+    assert env._variant() == _lib.STEP_TABLE
+    with pytest.raises(ValueError):
+        env.reset(seed=1, options={"similar_climate_counties": "intended", "reference_rng": True})
+    obs, _ = env.reset(options={"similar_climate_counties": "intended"})
+    idx = {k: v.cpu().numpy() for k, v in env._idx.items()}
+    st, o_ref = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"], idx["coef_col"],
+                                idx["coef_idx"], idx.get("budget"))
+    np.testing.assert_array_equal(obs.cpu().numpy(), o_ref.astype(np.float32))
+    rng = np.random.default_rng(2)
+    for _ in range(12):
+        act = rng.random(n) < 0.5
+        obs, rew, term, _, _ = env.step(torch.from_numpy(act).cuda())
+        o_ref, r_ref, d_ref, _, _ = orc.batch_step(store.feat, store.sig_code, weights.coef, st, act)
+        np.testing.assert_array_equal(obs.cpu().numpy(), o_ref.astype(np.float32))
+        np.testing.assert_allclose(rew.cpu().numpy(), r_ref, rtol=1e-5, atol=1e-10)

@@ -164,3 +164,23 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_intended_augmentation_moves_the_episode_to_a_similar_county(golden):
+    """`augment="intended"` (not the reference's behaviour): weather AND coefficient column are those
+    of a county drawn from the similar-county list; `augment=True` keeps the reference's quirk (Q6/Q7)."""
+    store, weights = golden.store(), golden.weights("std")
+    sp = EpisodeSampler(store, weights)
+    n = 4000
+    home = sp.draw_bulk(np.random.default_rng(3), n, None, False)
+    ref = sp.draw_bulk(np.random.default_rng(3), n, None, True)
+    new = sp.draw_bulk(np.random.default_rng(3), n, None, "intended")
+    np.testing.assert_array_equal(ref["loc"], home["loc"])          # Q7: the weather stays the original county's
+    assert (ref["coef_col"] < sp.n_similar[ref["list_idx"]]).all()  # Q6: an index inside the similar list
+    # intended: the drawn member of the ORIGINAL county's list, used consistently
+    np.testing.assert_array_equal(new["coef_col"], new["list_idx"])
+    np.testing.assert_array_equal(new["loc"], sp.list_to_data[new["list_idx"]])
+    for i in range(0, n, 97):
+        members = sp.groups.similar(sp.fips_list[int(home["list_idx"][i])])
+        assert members[int(ref["coef_col"][i])] == sp.fips_list[int(new["list_idx"][i])]
+    assert (new["list_idx"] != home["list_idx"]).mean() > 0.3  # it really moves

@@ -27,6 +27,12 @@ class EpisodeSampler:
         self.groups = ClimateGroups(store.conf_fips, store.conf_zone, self.fips_list)
         self.list_to_data = np.array([store.fips_index.get(f, -1) for f in self.fips_list], dtype=np.int64)
         self.n_similar = self.groups.counts_for(self.fips_list)
+        # CSR view of the similar-county lists in fips_list indices, for the "intended" augmentation:
+        # county i of the weights -> members[similar_start[i] : similar_start[i] + n_similar[i]]
+        lut = {f: i for i, f in enumerate(self.fips_list)}
+        self.similar_members = np.array([lut[f] for m in self.groups.members for f in m], dtype=np.int64)
+        self.similar_start = np.array([self.groups.offsets[self.groups.group_of[f]] if f in self.groups.group_of else 0
+                                       for f in self.fips_list], dtype=np.int64)
         self._valid_year_idx = np.array([store.year_index.get(int(y), -1) for y in self.valid_years], dtype=np.int64)
 
     # ---- one env, reference draw order ----------------------------------------------------
@@ -57,8 +63,12 @@ class EpisodeSampler:
                     year=int(year), s=s, y=y, coef_index=coef_index)
 
     # ---- many envs, one Generator -----------------------------------------------------------
-    def draw_bulk(self, rng: np.random.Generator, n: int, location=None, augment: bool = False):
+    def draw_bulk(self, rng: np.random.Generator, n: int, location=None, augment=False):
         """Vectorised draws (same distributions, one stream for the whole batch).
+
+        `augment`: False, True (the reference's behaviour: only the coefficient column changes, to the
+        index inside the similar-county list -- quirks Q6/Q7), or "intended" (NOT the reference: the
+        episode moves to a county drawn from the similar list -- its weather, its own coefficient column).
 
         `location`: None (uniform over the weights' county list), a FIPS string, or a
         sequence of n FIPS strings / fips_list indices.  Returns int32 arrays
@@ -85,6 +95,12 @@ class EpisodeSampler:
             if (n_c <= 0).any():
                 raise KeyError(self.fips_list[int(list_idx[np.argmax(n_c <= 0)])])
             coef_col = rng.integers(0, n_c)  # index inside the similar list (Q6)
+            if augment == "intended":  # the similar county itself: its weather and its own column
+                list_idx = self.similar_members[self.similar_start[list_idx] + coef_col]
+                coef_col = list_idx
+                loc = self.list_to_data[list_idx]
+                if (loc < 0).any():
+                    raise KeyError(self.fips_list[int(list_idx[np.argmax(loc < 0)])])
         else:
             coef_col = list_idx
         year = self._valid_year_idx[rng.integers(0, len(self.valid_years), size=n)]

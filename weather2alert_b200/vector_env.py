@@ -87,6 +87,8 @@ class HeatAlertVectorEnv:
         sp = self.sampler
         self._list_to_data = torch.from_numpy(sp.list_to_data).to(dev)
         self._n_similar = torch.from_numpy(sp.n_similar.astype(np.int64)).to(dev)
+        self._similar_start = torch.from_numpy(sp.similar_start).to(dev)
+        self._similar_members = torch.from_numpy(sp.similar_members).to(dev)
         self._valid_year_idx = torch.from_numpy(sp._valid_year_idx).to(dev)
         nd = self.store.n_days
         ok_c = sp.list_to_data >= 0
@@ -149,12 +151,14 @@ class HeatAlertVectorEnv:
                 raise KeyError((self.store.fips[int(src["loc"][bad])], self.store.years[int(src["year"][bad])]))
             return s
         augment = o.get("similar_climate_counties", self.similar_climate_counties)
-        self._canonical = not augment
+        self._canonical = (not augment) or augment == "intended"
         location = o.get("location")
         if o.get("reference_rng", False):
             # what gymnasium.vector.SyncVectorEnv([HeatAlertEnv]*N).reset(seed=s) does: env i seeds its
             # own PCG64 with s + i and draws in the reference order (env.py:143-177).  Host loop: for
             # parity and small batches.
+            if augment == "intended":
+                raise ValueError("reference_rng reproduces the reference's draws; 'intended' augmentation is not one of them")
             base_seed = o["reference_seed"]
             locs = location if isinstance(location, (list, tuple, np.ndarray)) else [location] * n
             rows, budgets = [], []
@@ -183,10 +187,16 @@ class HeatAlertVectorEnv:
             h = sp.draw_bulk(self._host_rng, n, location, False)["list_idx"]
             list_idx = torch.from_numpy(h.astype(np.int64)).to(dev)
         loc = self._list_to_data[list_idx]
+        no_similar = None
         if augment:  # index inside the similar-county list (env.py:117; Q6)
             n_c = self._n_similar[list_idx]
+            no_similar = n_c <= 0
             u = torch.rand(n, generator=self._gen, device=dev, dtype=torch.float64)
             coef_col = torch.minimum((u * n_c).long(), n_c - 1)
+            if augment == "intended":  # NOT the reference: the episode moves to the drawn similar county
+                list_idx = self._similar_members[self._similar_start[list_idx] + coef_col.clamp(min=0)]
+                coef_col = list_idx
+                loc = self._list_to_data[list_idx]
         else:
             coef_col = list_idx  # env.py:121
         year = self._valid_year_idx[self._randint(len(sp.valid_years), n)]  # env.py:125
@@ -194,7 +204,7 @@ class HeatAlertVectorEnv:
         if not self._all_episodes_exist or (augment and not self._augment_safe):
             bad = (loc < 0) | (year < 0)
             if augment:
-                bad |= self._n_similar[list_idx] <= 0
+                bad |= no_similar
             bad |= self._n_days_dev[(loc.clamp(min=0) * self.core.Y + year.clamp(min=0))] == 0
             if bool(bad.any()):  # the reference raises KeyError at env.py:127 / datautils.py:123
                 b = int(torch.nonzero(bad)[0])
@@ -229,7 +239,9 @@ class HeatAlertVectorEnv:
 
     # ---- reset --------------------------------------------------------------------------------
     def reset(self, *, seed: int | None = None, options: dict | None = None):
-        """`options` keys: `location` (FIPS, or a sequence of N), `similar_climate_counties`,
+        """`options` keys: `location` (FIPS, or a sequence of N), `similar_climate_counties` (False, True =
+        the reference's augmentation, or "intended" = the episode moves to a county drawn from the similar
+        list, weather and coefficient column alike -- a documented non-parity mode),
         `budget` (int or sequence), `sample_budget`, `sample_budget_type`, `reference_rng` (True: env i
         draws from its own ``default_rng(seed + i)`` in the reference's order, like a gymnasium
         SyncVectorEnv of reference envs), or `index_streams` (dict of int arrays `loc`, `year`,
