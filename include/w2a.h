@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define W2A_VERSION 100 /* 0.1.0 */
+#define W2A_VERSION 110 /* 0.1.1: + w2a_set_county_map / W2A_STEP_TABLE, w2a_rollout_policy */
 
 #define W2A_OK 0
 #define W2A_E_INVALID (-1)  /* bad argument (null pointer, size, dtype, variant) */
