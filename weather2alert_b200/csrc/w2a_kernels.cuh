@@ -559,9 +559,12 @@ __global__ void __launch_bounds__(32 * kCoopWarps, AHEAD > 4 ? 1 : W2A_COOP_MINB
 // =========================================================================================
 
 constexpr int kZPerLine = 6;     // (z_b, z_e) entries per 128-byte line, after the 32-byte head
-constexpr int kTableTaskWarps = 8;  // warps (= tasks) per CTA of logit_table_kernel
+#ifndef W2A_TABLE_TASK_WARPS
+#define W2A_TABLE_TASK_WARPS 4  // B200 sweep: 2 and 4 warps per CTA equal, 8 is 6 % slower, 16 a third slower
+#endif
+constexpr int kTableTaskWarps = W2A_TABLE_TASK_WARPS;  // warps (= tasks) per CTA of logit_table_kernel
 #ifndef W2A_TABLE_BUILD_MINBLOCKS
-#define W2A_TABLE_BUILD_MINBLOCKS 3
+#define W2A_TABLE_BUILD_MINBLOCKS 6  // x 4 warps = 24 warps/SM at 80 registers
 #endif
 
 // D(8x8) += A(8x4) * B(4x8) in float64 on the tensor cores (DMMA).  Fragments: A[lane/4][lane%4],
@@ -676,14 +679,17 @@ __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCK
 struct __align__(128) TableScratchWarp {
   float obs[32 * kObsDim];
 };
-constexpr int kTableWarps = 8;
+#ifndef W2A_TABLE_WARPS
+#define W2A_TABLE_WARPS 4  // warps per CTA of step_table_kernel (B200 sweep: 2..16 within 2 %)
+#endif
+constexpr int kTableWarps = W2A_TABLE_WARPS;
 constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScratchWarp));
 
 #ifndef W2A_TABLE_ROWS
 #define W2A_TABLE_ROWS 2  // rounds of observation-row gathers in flight per warp (B200 sweep: 2 with 4 CTAs/SM >= 8 with 3)
 #endif
 #ifndef W2A_TABLE_MINBLOCKS
-#define W2A_TABLE_MINBLOCKS 4
+#define W2A_TABLE_MINBLOCKS 8  // x 4 warps = 32 warps/SM at 64 registers
 #endif
 
 template <int ADT>
