@@ -66,9 +66,22 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_tables(years=N_YEARS, counties=S_COUNTIES, samples=P_SAMPLES):
+NN_FIPS_FILE = os.path.join(REPO, "weather2alert_b200", "data", "nn_full_medicare_all_fips.txt")
+
+
+def make_tables(years=N_YEARS, counties=S_COUNTIES, samples=P_SAMPLES, layout="linear"):
+    """layout="linear": 746 synthetic counties, weights for all of them (weights/linear: S = 746).
+    layout="nn": the store keeps its 746 counties but the checkpoint carries the 720-county `fips_list`
+    of the reference's weights/nn_full_medicare_all/config.yaml (BASELINE configs[2]): coefficient column
+    != store county, and 26 store counties have no column."""
     from weather2alert_b200 import synthetic
 
+    if layout == "nn":
+        with open(NN_FIPS_FILE) as fh:
+            nn_fips = fh.read().split()
+        fips, zones = synthetic.synthetic_counties(counties, seed=0, must_include=tuple(nn_fips))
+        store = synthetic.make_store(fips, list(range(2006, 2006 + years)), seed=1, zones=zones)
+        return store, synthetic.make_weights(nn_fips, samples, seed=2)
     fips, zones = synthetic.synthetic_counties(counties, seed=0)
     store = synthetic.make_store(fips, list(range(2006, 2006 + years)), seed=1, zones=zones)
     weights = synthetic.make_weights(fips, samples, seed=2)
@@ -83,7 +96,7 @@ def index_streams(store, weights, n, rank, augment, locality="interleaved"):
 
     rng = np.random.default_rng(1234 + rank)
     S = len(weights.fips_list)
-    list_idx = (np.arange(n, dtype=np.int64) + rank * n) % S
+    list_idx = (np.arange(n, dtype=np.int64) + rank * n) % S  # index into the weights' fips_list
     sp = EpisodeSampler(store, weights)
     s = sp.draw_bulk(rng, n, list_idx, augment)
     if locality == "sorted":
@@ -163,12 +176,174 @@ class ClockSampler(threading.Thread):
 # =================================================================================================
 # our arm
 # =================================================================================================
+class EnvSet:
+    """One device-resident env set on one GPU: buffers, the bound step call, and CUDA graphs of step
+    segments so that ANY --steps/--warmup runs from graphs: a segment is `l` consecutive steps that do
+    not cross the end of the summer, optionally followed by the reset of all envs; one graph per
+    distinct (l, reset) is captured before the timed region and replayed inside it."""
+
+    def __init__(self, core, idx, n, T, actions, variant, use_graph=True):
+        import torch
+
+        self.torch, self.core, self.idx, self.n, self.T, self.actions = torch, core, idx, n, T, actions
+        dev = core.device
+        self.state = core.alloc_state(n)
+        self.obs = torch.zeros((n, 29), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.term = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.rem = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.atb = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.step = core.bind_step(self.state, self.obs, self.reward, self.term, self.rem, self.atb, variant=variant)
+        self.use_graph, self.graphs, self.t, self.kernels = use_graph, {}, 0, 0
+
+    def reset(self):
+        i = self.idx
+        self.core.reset(self.state, self.obs, i["loc"], i["year"], i["coef_col"], i["coef_idx"], remaining=self.rem)
+        self.t = 0
+
+    def segments(self, t, k):
+        """(length, reset_after) pieces of k steps starting on day t; a finished summer is reset in place."""
+        out = []
+        while k > 0:
+            seg = min(k, self.T - t)
+            t += seg
+            k -= seg
+            out.append((seg, t == self.T))
+            if t == self.T:
+                t = 0
+        return out, t
+
+    def _launch(self, seg, reset_after):
+        for i in range(seg):
+            self.step(self.actions[i])
+        if reset_after:
+            self.reset()
+
+    def prepare(self, runs):
+        """Capture every graph the given sequence of run(k) calls will need, starting from the current day."""
+        if not self.use_graph:
+            return
+        torch, t = self.torch, self.t
+        need = []
+        for k in runs:
+            segs, t = self.segments(t, k)
+            need += [sg for sg in segs if sg not in self.graphs and sg not in need]
+        t_keep = self.t
+        for sg in need:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(*sg)
+            self.graphs[sg] = g
+        self.t = t_keep  # a capture executes nothing
+
+    def run(self, k):
+        segs, t_end = self.segments(self.t, k)
+        for sg in segs:
+            g = self.graphs.get(sg)
+            if g is not None:
+                g.replay()
+            else:
+                self._launch(*sg)
+            self.kernels += sg[0] + (1 if sg[1] else 0)
+        self.t = t_end
+
+
+def parity_gate(core, store, weights, variant, n=1 << 16, steps=12, seed=4321):
+    """before anything is timed, the tables the bench runs on (746 counties x 11 years
+    x 100 samples) are stepped on the GPU and by the C oracle (oracle/c/heat_oracle.c, the checker) from the
+    same index and action streams: observations, flags and counters bit-exact, rewards within 1e-5 relative."""
+    import torch
+
+    from oracle import c_oracle
+
+    if not c_oracle.available():
+        import __graft_entry__ as g
+
+        g.build_oracle()
+    dev = core.device
+    rng = np.random.default_rng(seed)
+    S = len(weights.fips_list)
+    col = (np.arange(n) % S).astype(np.int32)
+    loc = np.array([store.fips_index[f] for f in weights.fips_list], np.int32)[col]
+    year = rng.integers(0, store.shape[1], n).astype(np.int32)
+    p = rng.integers(0, weights.n_samples, n).astype(np.int32)
+    co = c_oracle.COracle(store.feat, store.sig_code, store.n_days, weights.coef, n)
+    o_ref = co.reset(loc, year, col, p)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    state = core.alloc_state(n)
+    obs = torch.zeros((n, 29), dtype=torch.float32, device=dev)
+    reward, term = torch.zeros(n, dtype=torch.float32, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev)
+    rem, atb = torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev)
+    core.reset(state, obs, d(loc), d(year), d(col), d(p), remaining=rem)
+
+    def same(a, b):  # bit-for-bit on values, NaN == NaN
+        return bool(np.array_equal(a, b, equal_nan=True))
+
+    obs_ok = same(obs.cpu().numpy(), o_ref.astype(np.float32))
+    flags_ok, max_rel = True, 0.0
+    for i in range(steps):
+        act = (rng.random(n) < (0.1, 0.5, 0.9)[i % 3]).astype(np.uint8)
+        core.step(state, d(act), obs, reward, term, rem, atb, variant=variant)
+        o_ref, r_ref, d_ref, rem_ref, atb_ref = co.step(act)
+        obs_ok &= same(obs.cpu().numpy(), o_ref.astype(np.float32))
+        flags_ok &= same(term.cpu().numpy(), d_ref) and same(rem.cpu().numpy(), rem_ref) and same(atb.cpu().numpy(), atb_ref)
+        r = reward.cpu().numpy().astype(np.float64)
+        err = np.abs(r - r_ref) / np.maximum(np.abs(r_ref), 1e-5)  # 1e-10 absolute floor of the 1e-5 relative bar
+        max_rel = max(max_rel, float(err.max()))
+    ok = bool(obs_ok and flags_ok and max_rel <= 1e-5)
+    return {"ok": ok, "envs": n, "steps": steps, "obs_bit_exact": bool(obs_ok), "flags_and_counters_exact": bool(flags_ok),
+            "max_reward_rel": max_rel, "reward_rtol": 1e-5,
+            "checker": "oracle/c/heat_oracle.c on the bench's own tables, same index and action streams"}
+
+
+def timed_steps(es, K, W, world, dist, target_ms=50.0, max_repeats=400):
+    """W warm-up steps, then R back-to-back regions of EXACTLY K steps, each bracketed by CUDA events on the
+    launching stream; barrier + synchronize on both sides of the whole sequence.  Returns the per-region times."""
+    import torch
+
+    dev = es.core.device
+    es.reset()
+    es.prepare([W, K])
+    es.run(W)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    p0.record()
+    es.run(K)  # pilot region (also warm-up): sizes the number of repeats
+    p1.record()
+    torch.cuda.synchronize()
+    reps = int(min(max_repeats, max(1, -(-target_ms // max(p0.elapsed_time(p1), 1e-3)))))
+    r_t = torch.tensor([reps], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(r_t, op=dist.ReduceOp.MAX)
+    reps = int(r_t.item())
+    es.prepare([K] * reps)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    k0 = es.kernels
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    ev[0].record()
+    for r in range(reps):
+        es.run(K)
+        ev[r + 1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    times = [ev[r].elapsed_time(ev[r + 1]) for r in range(reps)]
+    return times, (es.kernels - k0) // reps, w0, w1
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from weather2alert_b200 import _lib
     from weather2alert_b200.core import HeatAlertCore
+    from weather2alert_b200.distributed import RolloutStats, reduce_stats, summarize
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,153 +358,104 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    def all_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     wl = WORKLOADS[args.workload]
     n = args.envs_per_gpu or wl["envs_per_gpu"]
     K, W = args.steps, args.warmup
     t_setup = time.time()
-    store, weights = make_tables()
+    store, weights = make_tables(layout=args.weights_layout)
     core = HeatAlertCore(store, weights, dev)
+    torch.cuda.synchronize()
     s = index_streams(store, weights, n, rank, wl["augment"], args.locality)
     idx = {k: torch.from_numpy(v).to(dev) for k, v in s.items()}
     T = int(store.n_days.max())
-    variant = {"auto": _lib.STEP_AUTO, "thread": _lib.STEP_THREAD, "coop": _lib.STEP_COOP,
-               "table": _lib.STEP_TABLE}[args.variant]
-    if variant == _lib.STEP_AUTO:  # what HeatAlertVectorEnv does: the logit table for big non-augmented env sets
-        variant = core.choose_variant(n, canonical=not wl["augment"])
-    kernel_name = {_lib.STEP_TABLE: "logit_table_kernel + step_table_kernel", _lib.STEP_COOP: "step_coop_kernel",
-                   _lib.STEP_THREAD: "step_thread_kernel"}.get(
-        variant, "step_coop_kernel")
+    names = {"auto": _lib.STEP_AUTO, "thread": _lib.STEP_THREAD, "coop": _lib.STEP_COOP, "table": _lib.STEP_TABLE}
 
-    state = core.alloc_state(n)
-    obs = torch.zeros((n, 29), dtype=torch.float32, device=dev)
-    reward = torch.zeros(n, dtype=torch.float32, device=dev)
-    term = torch.zeros(n, dtype=torch.uint8, device=dev)
-    rem = torch.zeros(n, dtype=torch.int32, device=dev)
-    atb = torch.zeros(n, dtype=torch.uint8, device=dev)
+    def resolve(n_envs, augment):  # what HeatAlertVectorEnv does above the C ABI
+        v = names[args.variant]
+        return core.choose_variant(n_envs, canonical=not augment) if v == _lib.STEP_AUTO else v
+
+    variant = resolve(n, wl["augment"])
+    kernel_names = {_lib.STEP_TABLE: "step_table_kernel", _lib.STEP_COOP: "step_coop_kernel",
+                    _lib.STEP_THREAD: "step_thread_kernel", _lib.STEP_AUTO: "step_coop_kernel"}
+    kernel_name = kernel_names[variant]
+    log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s: {n} envs, tables "
+        f"{(core.x.numel() * 8 + core.w.numel() * 4) / 1e6:.0f} MB + {core.table_bytes / 1e9:.2f} GB precomputed "
+        f"(has_tables={core.has_tables}), variant {kernel_name}")
+
+    # ---- parity gate: nothing is timed unless the path agrees with the oracle on these very tables ----
+    parity = None
+    if not args.no_parity:
+        parity = parity_gate(core, store, weights, variant)
+        log(f"[rank {rank}] parity gate: {parity}")
+        ok_t = all_max(0.0 if parity["ok"] else 1.0)
+        if ok_t != 0.0:
+            if rank == 0:
+                emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "error": "parity gate failed",
+                      "parity": parity})
+            raise SystemExit(3)
+
     # uniform random actions, p = 0.5, one row per day of the summer, resident in HBM
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     actions = (torch.rand((T, n), generator=g, device=dev) < 0.5).to(torch.uint8)
-    step = core.bind_step(state, obs, reward, term, rem, atb, variant=variant)
-
-    def do_reset():
-        core.reset(state, obs, idx["loc"], idx["year"], idx["coef_col"], idx["coef_idx"], remaining=rem)
-
-    log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s: {n} envs, tables "
-        f"{(core.x.numel() * 8 + core.w.numel() * 4) / 1e6:.0f} MB")
 
     # ---- device-resident throughput: `value` ---------------------------------------------------
-    def run_steps(k, t):
-        """k steps starting at day t of the summer; a finished summer is reset in place (included)."""
-        for _ in range(k):
-            step(actions[t])
-            t += 1
-            if t == T:
-                do_reset()
-                t = 0
-        return t
-
-    # Replay one CUDA graph per summer (T step launches + the reset) instead of T+1 host launches:
-    # small batches are launch-latency bound (SURVEY H3) and even at 2^20 envs the Python-side
-    # launch loop costs a few per cent.
-    # graph replays cover whole summers; any other --steps/--warmup is honoured exactly with host launches
-    use_graph = (not args.no_graph) and args.steps % T == 0 and args.warmup % T == 0
-    graph = None
-    if use_graph:
-        do_reset()
-        run_steps(3, 0)  # warm every lazy path (occupancy queries, attributes) before capture
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for tt in range(T):
-                step(actions[tt])
-            do_reset()
-
-        def run_steps(k, t):  # noqa: F811 - graph version; whole summers only, remainder by launches
-            assert t == 0
-            while k >= T:
-                graph.replay()
-                k -= T
-            for i in range(k):
-                step(actions[i])
-            return k
-
-
-    do_reset()
-    t = run_steps(W, 0)
+    es = EnvSet(core, idx, n, T, actions, variant, use_graph=not args.no_graph)
+    es.reset()
+    es.run(3)  # warm every lazy path (occupancy queries, attributes) before any capture
+    torch.cuda.synchronize()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = core.launch_count
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    w0 = time.perf_counter()
-    ev0.record()
-    t = run_steps(K, t)
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    w1 = time.perf_counter()
+    times, launches, w0, w1 = timed_steps(es, K, W, world, dist)
     clocks.stop_flag.set()
-    launches = core.launch_count - launches0
-    if use_graph:
-        per_step = 2 if variant == _lib.STEP_TABLE else 1  # TABLE = table build + per-env kernel
-        launches += (K // T) * (T * per_step + 1)  # kernels replayed from the graph are not seen by the C-side counter
-    ms = ev0.elapsed_time(ev1)
-    ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_max = float(ms_t.item())
-    value = n * world * K / (ms_max * 1e-3)
+    ms_med = all_max(statistics.median(times))
+    value = n * world * K / (ms_med * 1e-3)
+    timing = {"repeats": len(times), "ms_region_median": ms_med, "ms_region_min": all_max(min(times)),
+              "ms_region_max": all_max(max(times)), "timed_ms_total": float(sum(times)),
+              "note": "R back-to-back regions of exactly K steps, one CUDA-event pair each; value and ms_per_step use "
+                      "the median region (max over ranks)"}
 
-    # return statistics of one full summer (untimed), then the only collective of the path:
-    # one all-reduce of the sufficient statistics (SURVEY.md 8(e); NCCL over NVLink when world > 1)
-    from weather2alert_b200.distributed import RolloutStats, summarize
+    # ---- the same episodes in (county, sample, year) slot order (`sort_episodes=True` of the vector env) ----
+    sorted_info = None
+    if args.locality == "interleaved" and not args.no_extras:
+        s2 = index_streams(store, weights, n, rank, wl["augment"], "sorted")
+        es2 = EnvSet(core, {k: torch.from_numpy(v).to(dev) for k, v in s2.items()}, n, T, actions, variant,
+                     use_graph=not args.no_graph)
+        t2, _, _, _ = timed_steps(es2, K, W, world, dist)
+        ms2 = all_max(statistics.median(t2))
+        sorted_info = {"value": n * world * K / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K,
+                       "roofline_frac": BYTES_STREAMING * n / (ms2 * 1e-3 / K) / 1e9 / load_peaks()[0],
+                       "note": "same multiset of episodes, env slots in (county, sample, year) order -- what "
+                               "HeatAlertVectorEnv(sort_episodes=True), its default for device-sampled resets, produces"}
+        del es2
 
-    rs = RolloutStats(n, dev)
-    do_reset()
-    for tt in range(T):
-        step(actions[tt])
-        rs.update(actions[tt], reward, term, atb)
-    stats = summarize(rs.reduce())
+    stats, rollout_info, theta = {}, None, None
+    if not args.no_extras:
+        # return statistics of one full summer (untimed), then the only collective of the path:
+        # one all-reduce of the sufficient statistics (NCCL over NVLink when world > 1)
+        rs = RolloutStats(n, dev)
+        es.reset()
+        for tt in range(T):
+            es.step(actions[tt])
+            rs.update(actions[tt], es.reward, es.term, es.atb)
+        stats = summarize(rs.reduce())
+        if int(round(stats["episodes"])) != n * world:
+            raise SystemExit(f"return statistics: {stats['episodes']} episodes reduced, expected {n * world}")
+        state, reward, term, atb = es.state, es.reward, es.term, es.atb
 
-    # the same summer through the episode-fused rollout kernel (one launch for all T steps, no
-    # observations): an extra, not the headline metric
-    ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
-    ro_stats = torch.zeros(15, dtype=torch.float64, device=dev)
-    ro_ms = []
-    for _ in range(3):
-        do_reset()
-        ep_ret.zero_()
-        ro_stats.zero_()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        r0.record()
-        core.rollout(state, T, ep_ret, actions=actions, stats=ro_stats)
-        r1.record()
-        torch.cuda.synchronize()
-        ro_ms.append(r0.elapsed_time(r1))
-    ro_t = torch.tensor([min(ro_ms[1:])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ro_t, op=dist.ReduceOp.MAX)
-    from weather2alert_b200.distributed import reduce_stats
+        def do_reset():
+            es.reset()
 
-    ro_sum = summarize(reduce_stats(ro_stats))
-    rollout_info = {"value": n * world * T / (float(ro_t.item()) * 1e-3), "unit": UNIT, "ms_per_rollout": float(ro_t.item()),
-                    "steps_per_rollout": T, "kernel": "rollout_kernel (episode-fused, obs elided)",
-                    "mean_return": ro_sum["mean_return"],
-                    "same_returns_as_stepping": bool(abs(ro_sum["mean_return"] - stats["mean_return"]) <= 1e-6 * abs(stats["mean_return"]))}
-
-    # the agent inside the launch: a logistic policy on the observation (w2a_rollout_policy), deterministic and
-    # stochastic, same summer; timed like the open-loop rollout
-    theta = torch.zeros(30, dtype=torch.float64)
-    theta[0], theta[6], theta[25], theta[28], theta[29] = 2.0, 0.004, 0.05, -0.3, -2.2  # heat_qi, dos, budget left, alerts in 2 weeks
-    theta = theta.to(dev)
-    for mode, stochastic in (("policy_deterministic", False), ("policy_stochastic", True)):
-        pms = []
+        # the same summer through the episode-fused rollout kernel (one launch for all T steps, no
+        # observations): an extra, not the headline metric
+        ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
+        ro_stats = torch.zeros(15, dtype=torch.float64, device=dev)
+        ro_ms = []
         for _ in range(3):
             do_reset()
             ep_ret.zero_()
@@ -337,22 +463,45 @@ def run_ours(args):
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             r0.record()
-            core.rollout_policy(state, T, ep_ret, theta, stochastic=stochastic, seed=99, stats=ro_stats)
+            core.rollout(state, T, ep_ret, actions=actions, stats=ro_stats)
             r1.record()
             torch.cuda.synchronize()
-            pms.append(r0.elapsed_time(r1))
-        p_t = torch.tensor([min(pms[1:])], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(p_t, op=dist.ReduceOp.MAX)
-        p_sum = summarize(reduce_stats(ro_stats))
-        rollout_info[mode] = {"value": n * world * T / (float(p_t.item()) * 1e-3), "ms_per_rollout": float(p_t.item()),
-                              "mean_return": p_sum["mean_return"], "alert_freq": p_sum.get("alert_freq"),
-                              "kernel": "rollout_kernel<POLICY> (logistic policy on the 29-slot observation, in the launch)"}
+            ro_ms.append(r0.elapsed_time(r1))
+        ro_t = all_max(min(ro_ms[1:]))
+        ro_sum = summarize(reduce_stats(ro_stats))
+        rollout_info = {"value": n * world * T / (ro_t * 1e-3), "unit": UNIT, "ms_per_rollout": ro_t,
+                        "steps_per_rollout": T, "kernel": "rollout_kernel (episode-fused, obs elided)",
+                        "mean_return": ro_sum["mean_return"],
+                        "same_returns_as_stepping": bool(abs(ro_sum["mean_return"] - stats["mean_return"]) <= 1e-6 * abs(stats["mean_return"]))}
+
+        # the agent inside the launch: a logistic policy on the observation (w2a_rollout_policy), deterministic and
+        # stochastic, same summer; timed like the open-loop rollout
+        theta = torch.zeros(30, dtype=torch.float64)
+        theta[0], theta[6], theta[25], theta[28], theta[29] = 2.0, 0.004, 0.05, -0.3, -2.2  # heat_qi, dos, budget left, alerts in 2 weeks
+        theta = theta.to(dev)
+        for mode, stochastic in (("policy_deterministic", False), ("policy_stochastic", True)):
+            pms = []
+            for _ in range(3):
+                do_reset()
+                ep_ret.zero_()
+                ro_stats.zero_()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                r0.record()
+                core.rollout_policy(state, T, ep_ret, theta, stochastic=stochastic, seed=99, stats=ro_stats)
+                r1.record()
+                torch.cuda.synchronize()
+                pms.append(r0.elapsed_time(r1))
+            p_t = all_max(min(pms[1:]))
+            p_sum = summarize(reduce_stats(ro_stats))
+            rollout_info[mode] = {"value": n * world * T / (p_t * 1e-3), "ms_per_rollout": p_t,
+                                  "mean_return": p_sum["mean_return"], "alert_freq": p_sum.get("alert_freq"),
+                                  "kernel": "rollout_kernel<POLICY> (logistic policy on the 29-slot observation, in the launch)"}
 
     # ---- policy in the loop (BASELINE configs[4] style): a small torch MLP policy on the observations and
     # the step kernel, a whole summer + reset captured in ONE CUDA graph (HeatAlertVectorEnv.graphed_rollout)
     policy_info = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.no_extras:
         try:
             from weather2alert_b200.vector_env import HeatAlertVectorEnv
 
@@ -377,16 +526,70 @@ def run_ours(args):
                 roll.replay()
             p1.record()
             torch.cuda.synchronize()
-            p_t = torch.tensor([p0.elapsed_time(p1) / 3], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(p_t, op=dist.ReduceOp.MAX)
-            policy_info = {"value": n * world * roll.steps / (float(p_t.item()) * 1e-3), "unit": UNIT,
-                           "ms_per_summer": float(p_t.item()), "steps_per_summer": roll.steps,
+            p_t = all_max(p0.elapsed_time(p1) / 3)
+            policy_info = {"value": n * world * roll.steps / (p_t * 1e-3), "unit": UNIT,
+                           "ms_per_summer": p_t, "steps_per_summer": roll.steps,
                            "policy": "torch MLP 29-64-1 (fp32 matmuls) on the observation tensor, deterministic threshold",
                            "mode": "policy forward + step kernel x 153 + reset in one CUDA graph"}
             del roll, venv
         except Exception as exc:  # an extra: never let it take the headline line down
             policy_info = {"error": repr(exc)[:300]}
+
+    # ---- BASELINE configs[3] and configs[4] per GPU beside the headline (SCALE then shows them at 8 GPUs):
+    # cfg4_2m = 2^21 augmented envs stepped; cfg5_8m = 2^23 envs, a full summer with the logistic policy inside
+    # the launch and the statistics all-reduced (the "policy-in-the-loop rollout with NCCL return-stat reduction")
+    other = {}
+    if not args.no_extras and not args.no_other_configs:
+        for name in ("cfg4_2m", "cfg5_8m"):
+            if name == args.workload:
+                continue
+            try:
+                wo = WORKLOADS[name]
+                no = wo["envs_per_gpu"]
+                so = index_streams(store, weights, no, rank, wo["augment"], "interleaved")
+                io = {k: torch.from_numpy(v).to(dev) for k, v in so.items()}
+                go = torch.Generator(device=dev).manual_seed(77 + rank)
+                ao = (torch.rand((T, no), generator=go, device=dev) < 0.5).to(torch.uint8)
+                vo = resolve(no, wo["augment"])
+                eo = EnvSet(core, io, no, T, ao, vo, use_graph=not args.no_graph)
+                eo.reset()
+                eo.run(3)
+                to, _, _, _ = timed_steps(eo, K, W, world, dist, target_ms=30.0)
+                mo = all_max(statistics.median(to))
+                entry = {"value": no * world * K / (mo * 1e-3), "unit": UNIT, "ms_per_step": mo / K, "envs_per_gpu": no,
+                         "envs_total": no * world, "kernel": kernel_names[vo], "augment": wo["augment"],
+                         "roofline_frac": BYTES_STREAMING * no / (mo * 1e-3 / K) / 1e9 / load_peaks()[0], "desc": wo["desc"]}
+                if name == "cfg5_8m":
+                    ret_o = torch.zeros(no, dtype=torch.float64, device=dev)
+                    st_o = torch.zeros(15, dtype=torch.float64, device=dev)
+                    pm = []
+                    for _ in range(2):
+                        eo.reset()
+                        ret_o.zero_()
+                        st_o.zero_()
+                        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        torch.cuda.synchronize()
+                        if world > 1:
+                            dist.barrier()
+                        r0.record()
+                        core.rollout_policy(eo.state, T, ret_o, theta, stochastic=True, seed=99, stats=st_o)
+                        red = reduce_stats(st_o)  # the NCCL all-reduce of the 15 sufficient statistics, inside the timed region
+                        r1.record()
+                        torch.cuda.synchronize()
+                        pm.append(r0.elapsed_time(r1))
+                    pt = all_max(min(pm))
+                    ps = summarize(red)
+                    if int(round(ps["episodes"])) != no * world:
+                        raise RuntimeError(f"policy rollout reduced {ps['episodes']} episodes, expected {no * world}")
+                    entry["policy_rollout_with_stat_allreduce"] = {
+                        "value": no * world * T / (pt * 1e-3), "unit": UNIT, "ms_per_summer": pt, "episodes": ps["episodes"],
+                        "mean_return": ps["mean_return"], "alert_freq": ps.get("alert_freq"),
+                        "kernel": "rollout_kernel<POLICY> (stochastic logistic policy) + all_reduce(float64[15])"}
+                other[name] = entry
+                del eo, io, ao
+                torch.cuda.empty_cache()
+            except Exception as exc:  # extras never take the headline down
+                other[name] = {"error": repr(exc)[:300]}
 
     # ---- end to end through the host-buffer C entry points: `e2e` ---------------------------------
     e2e = None
@@ -407,14 +610,31 @@ def run_ours(args):
         for i in range(ke):
             core.step_host(h_act[i % 8], h_obs, h_rew, h_term, h_rem, h_atb)
         torch.cuda.synchronize()
-        e_s = time.perf_counter() - e0
-        e_t = torch.tensor([e_s], dtype=torch.float64, device=dev)
+        e_s = all_max(time.perf_counter() - e0)
+        d2h = 29 * 4 + 4 + 1 + 4 + 1
+        # the link's own ceiling, measured here: one plain pinned device->host copy of the same byte count per step,
+        # all ranks at once (tools/pcie_bench.py sweeps 1..8 concurrent ranks)
+        blk = torch.empty(n * d2h, dtype=torch.uint8, device=dev)
+        hblk = torch.empty(n * d2h, dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            hblk.copy_(blk, non_blocking=True)
+        torch.cuda.synchronize()
         if world > 1:
-            dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * world * ke / float(e_t.item()), "unit": UNIT, "steps": ke,
+            dist.barrier()
+        l0 = time.perf_counter()
+        for _ in range(8):
+            hblk.copy_(blk, non_blocking=True)
+        torch.cuda.synchronize()
+        l_s = all_max(time.perf_counter() - l0)
+        link_gbs = n * d2h * 8 / l_s / 1e9
+        e2e = {"value": n * world * ke / e_s, "unit": UNIT, "steps": ke,
                "h2d_bytes_per_step": n * world * 1,
-               "d2h_bytes_per_step": n * world * (29 * 4 + 4 + 1 + 4 + 1),
+               "d2h_bytes_per_step": n * world * d2h,
+               "gbs_per_gpu": n * (d2h + 1) * ke / e_s / 1e9,
+               "link_gbs": link_gbs, "frac_of_link": n * (d2h + 1) * ke / e_s / 1e9 / link_gbs,
+               "link_note": f"link_gbs = plain pinned cudaMemcpyAsync D2H of {n * d2h >> 20} MiB blocks per GPU with all {world} ranks copying at once",
                "api": "w2a_step_host (C ABI, pinned host buffers, 3-stream chunked pipeline)"}
+        del blk, hblk
 
     if rank != 0:
         if world > 1:
@@ -423,7 +643,7 @@ def run_ours(args):
 
     # BASELINE configs[0] on the GPU: the single-env drop-in class, one summer, random policy
     single = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.no_extras:
         from weather2alert_b200 import HeatAlertEnv
 
         env1 = HeatAlertEnv(weights=weights, store=store, device=str(dev))
@@ -444,35 +664,23 @@ def run_ours(args):
 
     # BASELINE configs[1] beside the headline workload: 4 096 envs, one CUDA graph per summer, device-resident
     small = None
-    if not args.no_e2e and args.workload != "cfg2_4096" and world == 1:
+    if not args.no_extras and args.workload != "cfg2_4096" and world == 1:
         n2 = WORKLOADS["cfg2_4096"]["envs_per_gpu"]
         i2 = {k: torch.from_numpy(v).to(dev) for k, v in index_streams(store, weights, n2, 0, False, "interleaved").items()}
-        st2, ob2 = core.alloc_state(n2), torch.zeros((n2, 29), dtype=torch.float32, device=dev)
-        rw2, tm2 = torch.zeros(n2, dtype=torch.float32, device=dev), torch.zeros(n2, dtype=torch.uint8, device=dev)
-        step2 = core.bind_step(st2, ob2, rw2, tm2)
+        small = {"workload": "cfg2_4096", "unit": UNIT}
+        for vname, v2 in (("table", _lib.STEP_TABLE), ("coop", _lib.STEP_COOP)):
+            e2 = EnvSet(core, i2, n2, T, actions[:, :n2].contiguous(), v2)
+            e2.reset()
+            e2.run(3)
+            tm, _, _, _ = timed_steps(e2, T, T, 1, dist, target_ms=10.0)
+            small[f"ms_per_step_{vname}"] = statistics.median(tm) / T
+        v_auto = resolve(n2, False)
+        ms2 = small["ms_per_step_table" if v_auto == _lib.STEP_TABLE else "ms_per_step_coop"]
+        st2 = core.alloc_state(n2)
+        ob2 = torch.zeros((n2, 29), dtype=torch.float32, device=dev)
         act2 = actions[:, :n2].contiguous()
-
-        def summer2():
-            core.reset(st2, ob2, i2["loc"], i2["year"], i2["coef_col"], i2["coef_idx"])
-            for tt in range(T):
-                step2(act2[tt])
-
-        summer2()
-        torch.cuda.synchronize()
-        g2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g2):
-            summer2()
-        for _ in range(3):
-            g2.replay()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(10):
-            g2.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        ms2 = e0.elapsed_time(e1) / (10 * T)
         ret2 = torch.zeros(n2, dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r_ms = []
         for _ in range(3):
             core.reset(st2, ob2, i2["loc"], i2["year"], i2["coef_col"], i2["coef_idx"])
@@ -481,49 +689,57 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             r_ms.append(e0.elapsed_time(e1))
-        small = {"workload": "cfg2_4096", "value": n2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2,
-                 "rollout_value": n2 * T / (min(r_ms[1:]) * 1e-3),
-                 "note": "launch-latency bound (0.6 MB per step); the episode-fused rollout kernel is the fast path at this size"}
+        small.update({"value": n2 / (ms2 * 1e-3), "ms_per_step": ms2, "kernel": kernel_names[v_auto],
+                      "rollout_value": n2 * T / (min(r_ms[1:]) * 1e-3),
+                      "note": "launch-latency bound (0.6 MB per step); the episode-fused rollout kernel is the fast path at this size"})
 
     peak, peak_src = load_peaks()
-    sec_per_step = ms_max * 1e-3 / K
+    sec_per_step = ms_med * 1e-3 / K
     ach = BYTES_STREAMING * n / sec_per_step / 1e9
     ach_c = BYTES_CANONICAL * n / sec_per_step / 1e9
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_med / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": wl["desc"], "envs_per_gpu": n, "envs_total": n * world,
-                   "counties": S_COUNTIES, "years": N_YEARS, "days": T, "posterior_samples": P_SAMPLES,
-                   "weights": "linear-format synthetic (nn_* checkpoints share the layout and the path)",
+                   "counties": len(weights.fips_list), "store_counties": store.shape[0], "years": N_YEARS, "days": T,
+                   "posterior_samples": P_SAMPLES,
+                   "weights": ("nn_full_medicare_all layout: the 720-county fips_list of the reference's config.yaml, synthetic "
+                               "coefficients" if args.weights_layout == "nn" else
+                               "linear-format synthetic (nn_* checkpoints share the layout and the path)"),
                    "augment": wl["augment"],
-                   "mode": "one CUDA graph per summer (153 steps + reset)" if use_graph else "per-step launches",
+                   "mode": ("CUDA graphs of step segments (any --steps/--warmup), summer reset included"
+                            if not args.no_graph else "per-step launches"),
                    "locality": args.locality, "variant": args.variant, "kernel": kernel_name,
+                   "tables": f"whole-summer logit tables precomputed once ({core.table_bytes / 1e9:.2f} GB in HBM), no per-step build",
                    "parallelism": f"env-sharded x{world}, no step-time collective",
-                   "l2": "per-step streaming traffic (151 B x envs) exceeds the 126 MB L2 for >= 2^20 envs; "
-                         "tables (feature rows of the day + coefficients) are meant to stay L2-resident"},
+                   "l2": "per-step streaming traffic (151 B x envs) exceeds the 126 MB L2 for >= 2^20 envs: inputs larger than L2"},
         "gpu_launches": int(launches),
+        "timing": timing,
         "wall_s": w1 - w0,
         "clocks": clocks.summary(w0, w1),
+        "parity": parity,
         "e2e": e2e,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "bytes_per_env_step": BYTES_STREAMING, "peak_source": peak_src,
                      "kernel": kernel_name,
-                     "note": "achieved = streaming bytes (HBM-mandatory) x envs / mean step time over the timed region"},
+                     "note": "achieved = streaming bytes (HBM-mandatory) x envs / median step time over the timed regions"},
         "roofline_canonical_466B": {"achieved": ach_c, "frac": ach_c / peak,
                                     "note": "SURVEY 8(d) canonical 466 B/env-step; includes table gathers served from L2"},
+        "sorted": sorted_info,
         "return_stats": {**stats, "reduced_over": world},
         "rollout": rollout_info,
         "single_env": single,
         "configs_1_4096_envs": small,
         "policy_in_loop": policy_info,
+        "other_configs": other,
     }
     traffic_file = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as fh:
                 tr = json.load(fh)
-            if tr.get("workload") == args.workload and tr.get("envs") == n:
+            if tr.get("workload") == args.workload and tr.get("envs") == n and tr.get("kernel") == kernel_name:
                 out["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -724,6 +940,11 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every step from the host instead of replaying a CUDA graph per summer")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline, parity, e2e and cpu_baseline only")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the cfg4_2m / cfg5_8m extras")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate (profiling runs only)")
+    ap.add_argument("--weights-layout", choices=["linear", "nn"], default="linear",
+                    help="nn: the 720-county fips_list of weights/nn_full_medicare_all against the 746-county store")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-workers", type=int, default=0)

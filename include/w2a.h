@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define W2A_VERSION 110 /* 0.1.1: + w2a_set_county_map / W2A_STEP_TABLE, w2a_rollout_policy */
+#define W2A_VERSION 200 /* 0.2.0: + w2a_precompute_logits (whole-summer tables; W2A_STEP_TABLE no longer builds per step) */
 
 #define W2A_OK 0
 #define W2A_E_INVALID (-1)  /* bad argument (null pointer, size, dtype, variant) */
@@ -54,10 +54,11 @@ extern "C" {
 #define W2A_STEP_THREAD 1 /* one thread per env: the straightforward kernel, kept as the in-tree cross-check */
 #define W2A_STEP_COOP 2   /* 8 lanes per env: whole-line gathers, float64 fold in shared memory, TMA obs store;
                              small batches spread their warps over the SMs with every gather in flight at once */
-#define W2A_STEP_TABLE 3  /* two launches: today's logits of every (county, sample, year) once (a float64 GEMM per
-                             county on the FP64 tensor path), then one 128-byte record + one observation row per
-                             env; for big non-augmented env sets in lock step; needs w2a_set_county_map; envs the
-                             table does not cover are computed directly, so results never depend on the variant */
+#define W2A_STEP_TABLE 3  /* one 128-byte record of tabulated logits + one float32 observation row per env, from the
+                             whole-summer tables of w2a_precompute_logits; every env looks its own day up (no lock
+                             step needed); for env sets that step on their own county's coefficients -- envs the
+                             table does not cover (similar-county columns, quirk Q6) are computed directly, so
+                             results never depend on the variant */
 
 /* per-env budget value meaning "use the episode's historical budget"
  * (env.py:167-170: `self.ep["remaining_budget"].iloc[0]`). */
@@ -85,7 +86,7 @@ int w2a_destroy(w2a_ctx* ctx);
  *                                    -1e300; env.py:218), positions 26..31 must be 0.0
  *   n_days  dev uint8   [S*Y]        days in episode (county, year); 0 = no such episode
  *   budget0 dev int32   [S*Y]        historical `remaining_budget` of day 0 (env.py:169)
- * The tables are referenced, not copied, and must outlive their use.  S*Y*T < 2^24. */
+ * The tables are referenced, not copied, and must outlive their use.  S*Y*T < 2^24, Y <= 255, T <= 255. */
 int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const int32_t* budget0,
                      int S, int Y, int T);
 
@@ -94,16 +95,30 @@ int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const
  *   w  dev float32 [S_w*P, 64]; record (col*P + p) holds the coefficients of county column
  *      `col`, posterior sample `p` as (baseline, effectiveness) pairs: floats 0..47 the 24
  *      table features in record order, 48..55 must be 0 except float 51 = 1.0 (effectiveness
- *      coefficient of the gate column), 56..63 alert_lag1, alert_streak, remaining_budget, bias. */
+ *      coefficient of the gate column), 56..63 alert_lag1, alert_streak, remaining_budget, bias.
+ *      S_w * P < 2^24. */
 int w2a_set_coefs(w2a_ctx* ctx, const float* w, int P, int S_w);
 
 /* Optional: tell the library which feature-store county each coefficient column belongs to
  * (`fips_list[col]` -> index into the feature store, -1 = not in the store; the reference
- * keeps both keyed by FIPS string, env.py:75,121,127).  Enables W2A_STEP_TABLE; the context
- * allocates S_w*P*ceil(Y/6)*128 + S*Y*128 bytes of scratch for the per-step tables.  Call after
- * w2a_set_features / w2a_set_coefs and before w2a_reset (the reset marks the envs whose column
- * is their own county).  `col_to_loc` is dev int32 [S_w], referenced, not copied. */
+ * keeps both keyed by FIPS string, env.py:75,121,127).  Call after w2a_set_features /
+ * w2a_set_coefs and before w2a_reset (the reset marks the envs whose column is their own
+ * county).  `col_to_loc` is dev int32 [S_w], referenced, not copied (the call reads it once,
+ * synchronously, for the host-side checks of the *_host entry points). */
 int w2a_set_county_map(w2a_ctx* ctx, const int32_t* col_to_loc);
+
+/* Hoist the agent-independent part of the reward out of `step` (replaces the per-key loop of
+ * HeatAlertEnv._get_reward, env.py:206-217, for the 24 table features, the bias and the heat_qi
+ * gate): for every day of the summer, every (coefficient column, posterior sample) and every year
+ * of the column's county, z_b / z_e in float64 (a float64 GEMM per county and day on the FP64 tensor
+ * path), plus the float32 observation row of every day-row (the row copy of _get_obs, env.py:187).
+ * The context allocates T * S_w * P * ceil(Y/6) * 128 + S*Y*T * 128 bytes (w2a_precompute_bytes; 3.1 GB
+ * for 746 counties x 11 years x 153 days x 100 samples) and enqueues two kernels on `stream`; the
+ * tables are valid for work enqueued on that stream afterwards (or after a synchronisation).
+ * Enables W2A_STEP_TABLE.  Needs w2a_set_county_map; any later w2a_set_* call drops the tables.
+ * Returns W2A_E_NOMEM (nothing allocated) when the device does not have the room. */
+int w2a_precompute_logits(w2a_ctx* ctx, void* stream);
+size_t w2a_precompute_bytes(const w2a_ctx* ctx);
 
 /* Bytes of the opaque per-env state for `n` envs (16 bytes per env, two SoA planes). */
 size_t w2a_state_bytes(int64_t n);
@@ -173,7 +188,9 @@ int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const d
 /* ---- host-buffer entry points: the call a CPU-side RL loop makes ------------------
  * The context owns a device-resident env set; every call copies its inputs from and its
  * outputs to HOST memory (pinned for full PCIe speed), pipelined in chunks over several
- * streams, and returns after the outputs have landed.  Env sets of at most 1024 envs move their
+ * streams, and returns after the outputs have landed.  The step variant is chosen by the library: the
+ * tabulated logits (W2A_STEP_TABLE) when the tables exist and the host index streams of the resets show
+ * every env on its own county's column, else W2A_STEP_COOP.  Env sets of at most 1024 envs move their
  * actions and all step outputs through one pinned staging block (one copy each way), so the caller's
  * arrays may be ordinary pageable memory at no cost. */
 int w2a_host_envs_create(w2a_ctx* ctx, int64_t n);

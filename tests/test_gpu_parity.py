@@ -339,3 +339,142 @@ def test_table_variant_shapes_off_the_beaten_path(n_years, n_samples):
         assert_obs_equal(obs.cpu().numpy(), o_ref, f"step {i}")
         np.testing.assert_allclose(reward.cpu().numpy(), r_ref, rtol=REWARD_RTOL, atol=REWARD_ATOL)
         np.testing.assert_array_equal(term.cpu().numpy().astype(bool), d_ref)
+
+
+# ---- the benchmarked shape itself (746 counties x 11 years x 153 days x 100 samples) ------------------------
+@pytest.fixture(scope="module")
+def real_shape():
+    """The tables bench.py runs on, for both checkpoint layouts, and one core each (3.1 GB of tables per core)."""
+    import bench
+    from weather2alert_b200.core import HeatAlertCore
+
+    out = {}
+    for layout in ("linear", "nn"):
+        store, weights = bench.make_tables(layout=layout)
+        out[layout] = (store, weights, HeatAlertCore(store, weights, "cuda:0"))
+    yield out
+    out.clear()
+    torch.cuda.empty_cache()
+
+
+def _against_c_oracle(store, weights, core, n, steps, variants, seed, ragged=False):
+    """n envs, env i on column i mod S_w of the weights and that county's weather (canonical), stepped by every
+    variant and by oracle/c/heat_oracle.c from the same streams.  ragged: a third of the envs are reset mid-way,
+    so the envs are on different days of the summer (the table variant looks every env's own day up)."""
+    from oracle import c_oracle
+
+    rng = np.random.default_rng(seed)
+    Sw = len(weights.fips_list)
+    col = (np.arange(n) % Sw).astype(np.int32)
+    loc = np.array([store.fips_index[f] for f in weights.fips_list], np.int32)[col]
+    year = rng.integers(0, store.shape[1], n).astype(np.int32)
+    p = rng.integers(0, weights.n_samples, n).astype(np.int32)
+    acts = [(rng.random(n) < (0.1, 0.5, 0.9)[i % 3]).astype(np.uint8) for i in range(steps)]
+    co = c_oracle.COracle(store.feat, store.sig_code, store.n_days, weights.coef, n)
+    ref = [(co.reset(loc, year, col, p).astype(np.float32),)]
+    mask = (rng.random(n) < 0.33)
+    year2, p2 = rng.integers(0, store.shape[1], n).astype(np.int32), rng.integers(0, weights.n_samples, n).astype(np.int32)
+    for i, a in enumerate(acts):
+        if ragged and i == steps // 2:  # the oracle has no masked reset: rebuild the masked envs' state by hand
+            keep = {k: v.copy() for k, v in co.arr.items()}
+            co.reset(np.where(mask, loc, loc), np.where(mask, year2, year), col, np.where(mask, p2, p))
+            for k, v in co.arr.items():
+                sel = mask if v.ndim == 1 else mask[:, None]
+                v[...] = np.where(sel, v, keep[k])
+        o, r, d, rem, atb = co.step(a)
+        ref.append((o.astype(np.float32), r.copy(), d.copy(), rem.copy(), atb.copy()))
+    results = {}
+    for vname in variants:
+        state = core.alloc_state(n)
+        obs = torch.zeros((n, 29), device="cuda")
+        reward, term = torch.zeros(n, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+        rem, atb = torch.zeros(n, dtype=torch.int32, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+        core.reset(state, obs, _dev(loc), _dev(year), _dev(col), _dev(p), remaining=rem)
+        assert_obs_equal(obs.cpu().numpy(), ref[0][0], f"{vname} reset")
+        worst = 0.0
+        for i, a in enumerate(acts):
+            if ragged and i == steps // 2:
+                core.reset(state, obs, _dev(loc), _dev(np.where(mask, year2, year)), _dev(col), _dev(np.where(mask, p2, p)),
+                           mask=_dev(mask.astype(np.uint8)), remaining=rem)
+            core.step(state, _dev(a), obs, reward, term, rem, atb, variant=VARIANTS[vname])
+            o, r, d, rm, ab = ref[i + 1]
+            assert_obs_equal(obs.cpu().numpy(), o, f"{vname} step {i}")
+            got = reward.cpu().numpy()
+            np.testing.assert_allclose(got, r, rtol=REWARD_RTOL, atol=REWARD_ATOL, err_msg=f"{vname} step {i}")
+            worst = max(worst, float((np.abs(got - r) / np.maximum(np.abs(r), 1e-5)).max()))
+            np.testing.assert_array_equal(term.cpu().numpy(), d)
+            np.testing.assert_array_equal(rem.cpu().numpy(), rm)
+            np.testing.assert_array_equal(atb.cpu().numpy(), ab)
+        results[vname] = worst
+    return results
+
+
+def test_real_shape_million_envs_vs_c_oracle(real_shape):
+    """BASELINE configs[2] size on the bench's own tables: 2**20 envs x 20 steps, all three variants against the C
+    oracle (VERDICT r1 'weak' item 1: the benchmarked shape compared with the oracle, not with itself)."""
+    store, weights, core = real_shape["linear"]
+    assert core.has_tables
+    worst = _against_c_oracle(store, weights, core, 1 << 20, 20, ("table", "coop", "thread"), seed=7)
+    assert max(worst.values()) < 1e-5
+
+
+def test_real_shape_ragged_days_on_the_table_path(real_shape):
+    """Envs on different days of the summer (masked reset mid-way) keep using the tabulated logits: every env looks
+    its own day up in the whole-summer tables; checked against the C oracle on the real shape."""
+    store, weights, core = real_shape["linear"]
+    _against_c_oracle(store, weights, core, 40_000, 30, ("table",), seed=9, ragged=True)
+
+
+def test_nn_checkpoint_layout_720_counties(real_shape):
+    """BASELINE configs[2] literally: the 720-county `fips_list` of weights/nn_full_medicare_all/config.yaml
+    (tools/make_nn_fips.py) against a 746-county store -- coefficient column != store county, 26 counties of the
+    store without a column; all variants against the C oracle, and augmentation on that list."""
+    store, weights, core = real_shape["nn"]
+    assert len(weights.fips_list) == 720 and store.shape[0] == 746
+    c2l = core.col_to_loc.cpu().numpy()
+    assert (c2l >= 0).all() and len(set(c2l.tolist())) == 720 and (c2l != np.arange(720)).any()
+    _against_c_oracle(store, weights, core, 100_000, 12, ("table", "coop", "thread"), seed=11)
+    # similar-county augmentation (Q6): column = index inside the similar list -> not canonical, direct path
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200.sampling import EpisodeSampler
+
+    n = 5000
+    rng = np.random.default_rng(3)
+    sp = EpisodeSampler(store, weights)
+    s = sp.draw_bulk(rng, n, rng.integers(0, 720, n), True)
+    state, obs = core.alloc_state(n), torch.zeros((n, 29), device="cuda")
+    reward, term = torch.zeros(n, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+    core.reset(state, obs, *(_dev(s[k]) for k in ("loc", "year", "coef_col", "coef_idx")))
+    st, o_ref = orc.batch_reset(store.feat, store.sig_code, store.n_days, s["loc"], s["year"], s["coef_col"], s["coef_idx"])
+    assert_obs_equal(obs.cpu().numpy(), o_ref)
+    for i in range(6):
+        act = (rng.random(n) < 0.5).astype(np.uint8)
+        core.step(state, _dev(act), obs, reward, term, variant=(3, 2, 1)[i % 3])
+        o_ref, r_ref, d_ref, _, _ = orc.batch_step(store.feat, store.sig_code, weights.coef, st, act)
+        assert_obs_equal(obs.cpu().numpy(), o_ref, f"step {i}")
+        np.testing.assert_allclose(reward.cpu().numpy(), r_ref, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+
+
+def test_table_variant_needs_the_precomputed_tables(golden):
+    """W2A_STEP_TABLE without w2a_precompute_logits is refused loudly; with it, a later w2a_set_* drops the tables."""
+    import ctypes as C
+
+    from weather2alert_b200 import _lib
+    from weather2alert_b200.core import HeatAlertCore
+
+    core = HeatAlertCore(golden.store(), golden.weights("std"), "cuda:0", precompute=False)
+    assert not core.has_tables and core.table_bytes > 0
+    n = 64
+    state, obs = core.alloc_state(n), torch.zeros((n, 29), device="cuda")
+    z = torch.zeros(n, dtype=torch.int32, device="cuda")
+    core.reset(state, obs, z, z, z, z)
+    reward, term = torch.zeros(n, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+    with pytest.raises(_lib.W2AError, match="w2a_precompute_logits"):
+        core.step(state, z.to(torch.uint8), obs, reward, term, variant=_lib.STEP_TABLE)
+    assert core.precompute() and core.has_tables
+    core.step(state, z.to(torch.uint8), obs, reward, term, variant=_lib.STEP_TABLE)
+    torch.cuda.synchronize()
+    lib = _lib.lib()  # re-installing the coefficients invalidates the tables built from them
+    _lib.check(lib.w2a_set_coefs(core.ctx, C.c_void_p(core.w.data_ptr()), core.P, core.Sw), core.ctx)
+    with pytest.raises(_lib.W2AError):
+        core.step(state, z.to(torch.uint8), obs, reward, term, variant=_lib.STEP_TABLE)

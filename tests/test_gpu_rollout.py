@@ -254,3 +254,67 @@ def test_policy_rollout_matches_the_oracle_loop(n, stochastic):
     core.rollout_policy(st3, 153, r3, _dev(theta), stochastic=stochastic, seed=seed)
     mid = torch.from_numpy(store.n_days[idx["loc"], idx["year"]] > 3).cuda()
     assert torch.equal(st3.view(2, n, 8)[:, mid], keep.view(2, n, 8)[:, mid]) and not r3[mid].any()
+
+
+@pytest.mark.parametrize("T", [200, 255])
+def test_rollout_long_summers_quantile_days(T):
+    """summers longer than 192 days (the C ABI allows T <= 255) used to overrun the
+    rollout kernel's shared issued-alert bits.  A synthetic T-day store, one launch for the whole summer:
+    returns against the oracle's loop and the a50/a80/a100 quantile days against a host recount."""
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200 import schema, synthetic
+    from weather2alert_b200.core import HeatAlertCore
+    from weather2alert_b200.distributed import STAT_NAMES
+    from weather2alert_b200.store import FeatureStore
+
+    S, Y, P, n = 6, 2, 4, 333
+    rng = np.random.default_rng(T)
+    fips, zones = synthetic.synthetic_counties(S, seed=3)
+    base = synthetic.make_store(fips, [2006, 2007], seed=4, zones=zones)
+    reps = -(-T // schema.MAX_DAYS)
+    feat = np.tile(base.feat, (1, 1, reps, 1))[:, :, :T].copy()
+    sig = np.tile(base.sig_code, (1, 1, reps))[:, :, :T].copy()
+    n_days = np.full((S, Y), T, np.uint8)
+    n_days[0, 0] = 193  # just past the old 192-day limit
+    store = FeatureStore(fips=base.fips, years=base.years, n_days=n_days, feat=feat, sig_code=sig,
+                         sig_labels=base.sig_labels, conf_fips=base.conf_fips, conf_zone=base.conf_zone)
+    weights = synthetic.make_weights(fips, P, seed=5)
+    core = HeatAlertCore(store, weights, "cuda:0")
+    idx = {k: v.astype(np.int32) for k, v in dict(loc=rng.integers(0, S, n), year=rng.integers(0, Y, n),
+                                                    coef_col=rng.integers(0, S, n), coef_idx=rng.integers(0, P, n),
+                                                    budget=rng.integers(20, 60, n)).items()}
+    acts = (rng.random((T, n)) < 0.3).astype(np.uint8)
+    acts[-30:] |= (rng.random((30, n)) < 0.5).astype(np.uint8)  # alerts late in the summer: days past 192 matter
+    st = core.alloc_state(n)
+    obs = torch.zeros((n, 29), device="cuda")
+    core.reset(st, obs, *(_dev(idx[k]) for k in ("loc", "year", "coef_col", "coef_idx")), budget=_dev(idx["budget"]))
+    ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    stats = torch.zeros(15, dtype=torch.float64, device="cuda")
+    core.rollout(st, T, ret, actions=_dev(acts), stats=stats)
+    ost, _ = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"], idx["coef_col"],
+                             idx["coef_idx"], idx["budget"])
+    ret_ref, alive = np.zeros(n), np.ones(n, bool)
+    issued = [[] for _ in range(n)]
+    for k in range(T):
+        before = ost["budget"] - ost["hist"].sum(axis=1)
+        t_before = ost["t"].copy()
+        _, r, dn, rem, _ = orc.batch_step(store.feat, store.sig_code, weights.coef, ost, acts[k])
+        for i in np.flatnonzero(alive & ((before - rem) > 0)):
+            issued[i].append(int(t_before[i]))
+        ret_ref += np.where(alive, r, 0.0)
+        alive &= ~dn
+    assert not alive.any()
+    np.testing.assert_allclose(ret.cpu().numpy(), ret_ref, rtol=1e-9, atol=1e-12)
+    s = dict(zip(STAT_NAMES, stats.cpu().tolist()))
+    a50 = a80 = a100 = cnt = 0
+    for d in issued:
+        if d:
+            d = np.array(d)
+            cum = np.arange(1, len(d) + 1)
+            a50 += d[np.argmax(2 * cum >= len(d))]
+            a80 += d[np.argmax(5 * cum >= 4 * len(d))]
+            a100 += d[-1]
+            cnt += 1
+    assert max(max(d) for d in issued if d) > 192
+    assert (s["a50_sum"], s["a80_sum"], s["a100_sum"], s["a_count"]) == (a50, a80, a100, cnt)
+    assert s["episodes"] == n

@@ -137,7 +137,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()  # ImportError if the extension was not built
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.w2a_version() == 110
+    assert lib.w2a_version() == 200
     assert lib.w2a_state_bytes(10) == 160
     # error paths that need no GPU
     assert lib.w2a_create(0, None) == -1
@@ -146,14 +146,22 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_auto_variant_rule_above_the_abi():
-    """TABLE only for big batches of envs on their own county's coefficients (the C library's AUTO never picks it)."""
+    """TABLE only for envs on their own county's coefficients, with the whole-summer tables built (the C library's
+    AUTO never picks it)."""
+    import types
+
     from weather2alert_b200 import _lib
     from weather2alert_b200.core import HeatAlertCore
 
-    pick = lambda n, canonical: HeatAlertCore.choose_variant(HeatAlertCore, n, canonical)  # noqa: E731 - no GPU needed
+    def pick(n, canonical, has_tables=True):  # no GPU needed
+        stub = types.SimpleNamespace(has_tables=has_tables, TABLE_MIN_ENVS=HeatAlertCore.TABLE_MIN_ENVS)
+        return HeatAlertCore.choose_variant(stub, n, canonical)
+
     assert pick(1 << 20, True) == _lib.STEP_TABLE and pick(1 << 23, True) == _lib.STEP_TABLE
     assert pick(1 << 20, False) == _lib.STEP_AUTO  # similar-county augmentation
-    assert pick(4096, True) == _lib.STEP_AUTO and pick(HeatAlertCore.TABLE_MIN_ENVS - 1, True) == _lib.STEP_AUTO
+    assert pick(1 << 20, True, has_tables=False) == _lib.STEP_AUTO  # no room for the tables on the device
+    assert pick(HeatAlertCore.TABLE_MIN_ENVS, True) == _lib.STEP_TABLE
+    assert pick(HeatAlertCore.TABLE_MIN_ENVS - 1, True) == _lib.STEP_AUTO
     assert _lib.POLICY_LEN == 30 and _lib.STEP_TABLE == 3
 
 

@@ -29,6 +29,8 @@ SIGNATURES = {
     "w2a_set_features": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "w2a_set_coefs": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "w2a_set_county_map": (C.c_int, [_P, _P]),
+    "w2a_precompute_logits": (C.c_int, [_P, _P]),
+    "w2a_precompute_bytes": (C.c_size_t, [_P]),
     "w2a_state_bytes": (C.c_size_t, [C.c_int64]),
     "w2a_reset": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "w2a_step": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int]),

@@ -24,7 +24,7 @@ def _ptr(t):
 class HeatAlertCore:
     """One C context on one GPU with the feature store and coefficient tables installed."""
 
-    def __init__(self, store: FeatureStore, weights: RewardWeights, device="cuda:0"):
+    def __init__(self, store: FeatureStore, weights: RewardWeights, device="cuda:0", precompute: bool = True):
         self._lib = _lib.lib()  # raises ImportError when the extension is not built
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -48,10 +48,28 @@ class HeatAlertCore:
         _lib.check(self._lib.w2a_set_features(ctx, _ptr(self.x), _ptr(self.n_days), _ptr(self.budget0),
                                               S, Y, T), ctx)
         _lib.check(self._lib.w2a_set_coefs(ctx, _ptr(self.w), self.P, self.Sw), ctx)
-        # feature-store county of every coefficient column: enables the per-step logit table (STEP_TABLE)
+        # feature-store county of every coefficient column (the reference keys both by FIPS string,
+        # env.py:75,121,127); -1 = the weights know a county the store does not (e.g. a 720-county
+        # `nn_*` fips_list against a bigger store, or the other way round)
         col_to_loc = np.array([store.fips_index.get(f, -1) for f in weights.fips_list], dtype=np.int32)
         self.col_to_loc = torch.from_numpy(col_to_loc).to(dev)
         _lib.check(self._lib.w2a_set_county_map(ctx, _ptr(self.col_to_loc)), ctx)
+        # whole-summer logit tables (`w2a_precompute_logits`): the agent-independent part of
+        # `_get_reward` (env.py:206-217) evaluated once here instead of in every step; enables STEP_TABLE
+        self.has_tables = False
+        self.table_bytes = int(self._lib.w2a_precompute_bytes(ctx))
+        if precompute:
+            self.precompute()
+
+    def precompute(self) -> bool:
+        """Build the whole-summer tables; False (and STEP_TABLE stays unavailable) when the device has no room."""
+        rc = self._lib.w2a_precompute_logits(self.ctx, self._stream())
+        if rc == -4:  # W2A_E_NOMEM: nothing was allocated, the other variants still work
+            self.has_tables = False
+            return False
+        _lib.check(rc, self.ctx)
+        self.has_tables = True
+        return True
 
     def __del__(self):
         ctx = getattr(self, "ctx", None)
@@ -108,16 +126,15 @@ class HeatAlertCore:
                                       _ptr(state), _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(remaining),
                                       _ptr(at_budget), variant), self.ctx)
 
-    # Below this many envs the fixed cost of building the per-step logit table (~13 us on a B200 for
-    # 746 columns x 100 samples x 11 years) outweighs the gathers it saves (COOP: ~52 ns, TABLE: ~37 ns
-    # per 1000 envs).
-    TABLE_MIN_ENVS = 3 << 18
+    # Below this many envs COOP's small-batch instance (every gather of a group in flight at once, warps
+    # spread over the SMs) is the faster launch; the tables themselves cost nothing per step any more.
+    TABLE_MIN_ENVS = 2048
 
     def choose_variant(self, n: int, canonical: bool) -> int:
-        """Resolve STEP_AUTO above the C ABI: TABLE for large batches whose envs all use their own
-        county's coefficient column (no similar-county substitution) and march in lock step -- the C
-        library cannot know either, so its own AUTO only picks between THREAD and COOP."""
-        if canonical and n >= self.TABLE_MIN_ENVS:
+        """Resolve STEP_AUTO above the C ABI: TABLE (tabulated logits, one record + one row per env) when
+        the tables exist and every env uses its own county's coefficient column (no similar-county
+        substitution -- the C library cannot know that, so its own AUTO is COOP)."""
+        if canonical and getattr(self, "has_tables", False) and n >= self.TABLE_MIN_ENVS:
             return _lib.STEP_TABLE
         return _lib.STEP_AUTO
 

@@ -10,8 +10,10 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "w2a_kernels.cuh"
 
@@ -33,6 +35,11 @@ struct HostEnvs {
   uint8_t* at_budget = nullptr;
   int32_t* idx = nullptr;  // 5 planes of n int32: loc, year, coef_col, coef_idx, budget
   uint8_t* mask = nullptr;
+  // which envs step on their own county's coefficient column (decided from the host index streams of the
+  // resets): when all do and the whole-summer tables exist, the step runs the TABLE variant
+  std::vector<uint8_t> noncanon;
+  int64_t n_noncanon = 0;
+  bool ever_reset = false;
   cudaStream_t streams[kHostStreams] = {};
   // small batches (n <= kHostPackedMax): the step outputs are one device block [obs | reward | remaining |
   // terminated | at_budget] that comes back with ONE copy into a pinned staging block (and the actions go
@@ -58,7 +65,9 @@ struct w2a_ctx {
   bool have_coefs = false;
   int64_t launches = 0;
   HostEnvs* host = nullptr;
-  void* table_scratch = nullptr;  // z_tab | xobs_t | t_cell, owned by the context (step variant TABLE)
+  void* table_scratch = nullptr;  // z_all | x32, owned by the context (step variant TABLE, w2a_precompute_logits)
+  std::vector<int32_t> col_to_loc_host;  // host copy of the county map (canonical check of the *_host resets)
+  bool pdl = true;                // step kernels are launched with programmatic stream serialization (W2A_PDL=0: off)
   const void* occ_key[kMaxKernels] = {};  // occupancy (CTAs per SM) of each kernel launched so far
   int occ_val[kMaxKernels] = {};
   int n_occ = 0;
@@ -82,6 +91,25 @@ int fail(w2a_ctx* ctx, int code, const char* fmt, ...) {
     if (err__ != cudaSuccess)                                                            \
       return fail((ctx), W2A_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(err__)); \
   } while (0)
+
+// Launch `kernel`, optionally as a programmatic dependent launch: with the attribute set the kernel may
+// become resident while the previous launch on the stream drains; the step kernels execute
+// griddepcontrol.wait before they read anything, so the data dependency is kept (a no-op otherwise).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Persistent-style grid: enough CTAs to fill every SM at the kernel's occupancy, never
 // more than the work needs; the kernels walk the envs with a grid-stride loop.
@@ -111,23 +139,14 @@ template <int ADT>
 int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int variant) {
   int grid = 0;
   if (variant == W2A_STEP_TABLE) {
-    // today's logit table for every (county, posterior sample, year), then the per-env kernel
-    const int table_tasks = ctx->tb.Sw * ((ctx->tb.P + 7) / 8) + (ctx->tb.Sw + 3) / 4;
-    const int table_grid = (table_tasks + w2a::kTableTaskWarps - 1) / w2a::kTableTaskWarps;
-    w2a::logit_table_kernel<<<table_grid, 32 * w2a::kTableTaskWarps, 0, st>>>(ctx->tb, a.st_mut);
-    ctx->launches++;
     constexpr int kBlock = 32 * w2a::kTableWarps;
     int rc = grid_for(ctx, w2a::step_table_kernel<ADT>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);
     if (rc) return rc;
-    w2a::step_table_kernel<ADT><<<grid, kBlock, w2a::kTableSmemBytes, st>>>(a);
-    ctx->launches++;
-    W2A_CUDA(ctx, cudaGetLastError());
-    return W2A_OK;
-  }
-  if (variant == W2A_STEP_THREAD) {
+    W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT>, grid, kBlock, w2a::kTableSmemBytes, st, ctx->pdl, a));
+  } else if (variant == W2A_STEP_THREAD) {
     int rc = grid_for(ctx, w2a::step_thread_kernel<ADT>, 128, 0, 128, a.n, &grid);
     if (rc) return rc;
-    w2a::step_thread_kernel<ADT><<<grid, 128, 0, st>>>(a);
+    W2A_CUDA(ctx, launch_kernel(w2a::step_thread_kernel<ADT>, grid, 128, 0, st, ctx->pdl, a));
   } else {
     constexpr int kBlock = 32 * w2a::kCoopWarps;
     int rc = grid_for(ctx, w2a::step_coop_kernel<ADT>, kBlock, w2a::kCoopSmemBytes, kBlock, a.n, &grid);
@@ -140,9 +159,10 @@ int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int varia
       rc = grid_for(ctx, w2a::step_coop_kernel<ADT, 7>, kBlock, w2a::kCoopSmemBytes, kBlock, a.n, &unused);
       if (rc) return rc;
       const int small_grid = static_cast<int>((groups + warps - 1) / warps);
-      w2a::step_coop_kernel<ADT, 7><<<small_grid, 32 * warps, warps * sizeof(w2a::WarpScratch), st>>>(a);
+      W2A_CUDA(ctx, launch_kernel(w2a::step_coop_kernel<ADT, 7>, small_grid, 32 * warps, warps * sizeof(w2a::WarpScratch), st,
+                                  ctx->pdl, a));
     } else {
-      w2a::step_coop_kernel<ADT><<<grid, kBlock, w2a::kCoopSmemBytes, st>>>(a);
+      W2A_CUDA(ctx, launch_kernel(w2a::step_coop_kernel<ADT>, grid, kBlock, w2a::kCoopSmemBytes, st, ctx->pdl, a));
     }
   }
   ctx->launches++;
@@ -156,8 +176,8 @@ int step_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const void* action, in
   if (variant == W2A_STEP_AUTO) variant = W2A_STEP_COOP;  // faster than THREAD at every batch size, n = 1 included
   if (variant != W2A_STEP_THREAD && variant != W2A_STEP_COOP && variant != W2A_STEP_TABLE)
     return fail(ctx, W2A_E_INVALID, "w2a_step: unknown variant %d", variant);
-  if (variant == W2A_STEP_TABLE && !ctx->tb.z_tab)
-    return fail(ctx, W2A_E_NOTREADY, "w2a_step: W2A_STEP_TABLE needs w2a_set_county_map first");
+  if (variant == W2A_STEP_TABLE && !ctx->tb.z_all)
+    return fail(ctx, W2A_E_NOTREADY, "w2a_step: W2A_STEP_TABLE needs w2a_set_county_map + w2a_precompute_logits first");
   w2a::StepArgs a;
   a.tb = ctx->tb;
   a.st_static = st_static;
@@ -244,6 +264,8 @@ int w2a_create(int device, w2a_ctx** out) {
   if (!ctx) return fail(nullptr, W2A_E_NOMEM, "w2a_create: out of host memory");
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  const char* pdl_env = std::getenv("W2A_PDL");  // tuning switch: W2A_PDL=0 launches the step kernels fully serialised
+  ctx->pdl = !(pdl_env && pdl_env[0] == '0');
   *out = ctx;
   return W2A_OK;
 }
@@ -254,17 +276,31 @@ int w2a_destroy(w2a_ctx* ctx) {
   if (ctx->table_scratch) {
     cudaSetDevice(ctx->device);
     cudaFree(ctx->table_scratch);
+    ctx->table_scratch = nullptr;
   }
   delete ctx;
   return W2A_OK;
+}
+
+// the whole-summer tables belong to one (features, coefficients, county map) triple
+static void drop_tables(w2a_ctx* ctx) {
+  if (ctx->table_scratch) {
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->table_scratch);
+    ctx->table_scratch = nullptr;
+  }
+  ctx->tb.z_all = nullptr;
+  ctx->tb.x32 = nullptr;
+  ctx->tb.z_lines = 0;
+  ctx->tb.z_day_lines = 0;
 }
 
 int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const int32_t* budget0, int S, int Y,
                      int T) {
   if (!ctx) return W2A_E_INVALID;
   if (!x || !n_days || !budget0) return fail(ctx, W2A_E_INVALID, "w2a_set_features: NULL table");
-  if (S <= 0 || Y <= 0 || T <= 0 || T > 255)
-    return fail(ctx, W2A_E_INVALID, "w2a_set_features: bad shape S=%d Y=%d T=%d (T<=255)", S, Y, T);
+  if (S <= 0 || Y <= 0 || T <= 0 || T > 255 || Y > 255)
+    return fail(ctx, W2A_E_INVALID, "w2a_set_features: bad shape S=%d Y=%d T=%d (Y<=255, T<=255)", S, Y, T);
   if (static_cast<int64_t>(S) * Y * T >= (int64_t{1} << 24))
     return fail(ctx, W2A_E_INVALID, "w2a_set_features: S*Y*T=%lld rows exceed the 24-bit row index",
                 static_cast<long long>(static_cast<int64_t>(S) * Y * T));
@@ -277,8 +313,9 @@ int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const
   ctx->tb.Y = Y;
   ctx->tb.T = T;
   ctx->have_features = true;
-  ctx->tb.col_to_loc = nullptr;  // a county map (and its scratch) belongs to one set of tables
-  ctx->tb.z_tab = nullptr;
+  ctx->tb.col_to_loc = nullptr;  // a county map (and the tables built from it) belongs to one set of tables
+  ctx->col_to_loc_host.clear();
+  drop_tables(ctx);
   return W2A_OK;
 }
 
@@ -287,14 +324,16 @@ int w2a_set_coefs(w2a_ctx* ctx, const float* w, int P, int S_w) {
   if (!w || P <= 0 || S_w <= 0) return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: bad argument");
   if (reinterpret_cast<uintptr_t>(w) & 127)
     return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: the table must be 128-byte aligned");
-  if (static_cast<int64_t>(P) * S_w >= (int64_t{1} << 31))
-    return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: P*S_w too large");
+  if (static_cast<int64_t>(P) * S_w >= (int64_t{1} << 24))
+    return fail(ctx, W2A_E_INVALID, "w2a_set_coefs: P*S_w=%lld records exceed the 24-bit record index",
+                static_cast<long long>(static_cast<int64_t>(P) * S_w));
   ctx->tb.w = w;
   ctx->tb.P = P;
   ctx->tb.Sw = S_w;
   ctx->have_coefs = true;
   ctx->tb.col_to_loc = nullptr;
-  ctx->tb.z_tab = nullptr;
+  ctx->col_to_loc_host.clear();
+  drop_tables(ctx);
   return W2A_OK;
 }
 
@@ -303,30 +342,71 @@ int w2a_set_county_map(w2a_ctx* ctx, const int32_t* col_to_loc) {
   if (!ctx->have_features || !ctx->have_coefs)
     return fail(ctx, W2A_E_NOTREADY, "w2a_set_county_map: call w2a_set_features and w2a_set_coefs first");
   if (!col_to_loc) return fail(ctx, W2A_E_INVALID, "w2a_set_county_map: NULL map");
-  if (static_cast<int64_t>(ctx->tb.Sw) * ctx->tb.P >= (int64_t{1} << 24) || ctx->tb.P >= (1 << 16) ||
-      ctx->tb.T >= (1 << 16) || ctx->tb.Y >= (1 << 14))
-    return fail(ctx, W2A_E_INVALID, "w2a_set_county_map: tables too large for the per-step logit table");
   W2A_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (ctx->table_scratch) {
-    W2A_CUDA(ctx, cudaFree(ctx->table_scratch));
-    ctx->table_scratch = nullptr;
-    ctx->tb.z_tab = nullptr;
-  }
-  const w2a::Tables& tb = ctx->tb;
-  const int z_lines = (tb.Y + w2a::kZPerLine - 1) / w2a::kZPerLine;
-  const size_t z_bytes = static_cast<size_t>(tb.Sw) * tb.P * z_lines * 128;
-  const size_t o_bytes = static_cast<size_t>(tb.S) * tb.Y * 32 * sizeof(float);
-  W2A_CUDA(ctx, cudaMalloc(&ctx->table_scratch, z_bytes + o_bytes + 256));
-  W2A_CUDA(ctx, cudaMemset(ctx->table_scratch, 0, z_bytes + o_bytes + 256));
-  char* base = static_cast<char*>(ctx->table_scratch);
-  ctx->tb.z_tab = reinterpret_cast<float4*>(base);
-  ctx->tb.z_lines = z_lines;
-  ctx->tb.xobs_t = reinterpret_cast<float*>(base + z_bytes);
-  ctx->tb.t_cell = reinterpret_cast<int*>(base + z_bytes + o_bytes);
+  drop_tables(ctx);
+  ctx->col_to_loc_host.resize(static_cast<size_t>(ctx->tb.Sw));
+  W2A_CUDA(ctx, cudaMemcpy(ctx->col_to_loc_host.data(), col_to_loc, sizeof(int32_t) * ctx->tb.Sw, cudaMemcpyDeviceToHost));
+  for (int32_t s : ctx->col_to_loc_host)
+    if (s < -1 || s >= ctx->tb.S) {
+      ctx->col_to_loc_host.clear();
+      return fail(ctx, W2A_E_INVALID, "w2a_set_county_map: county %d not in [-1, %d)", s, ctx->tb.S);
+    }
   ctx->tb.col_to_loc = col_to_loc;
-  const unsigned long long one40 = 1ull << 40;
-  ctx->tb.magic_T = (one40 + tb.T - 1) / tb.T;
-  ctx->tb.magic_Y = (one40 + tb.Y - 1) / tb.Y;
+  return W2A_OK;
+}
+
+size_t w2a_precompute_bytes(const w2a_ctx* ctx) {
+  if (!ctx || !ctx->have_features || !ctx->have_coefs) return 0;
+  const w2a::Tables& tb = ctx->tb;
+  const size_t z_lines = static_cast<size_t>((tb.Y + w2a::kZPerLine - 1) / w2a::kZPerLine);
+  const size_t z_bytes = static_cast<size_t>(tb.T) * tb.Sw * tb.P * z_lines * 128;
+  const size_t o_bytes = static_cast<size_t>(tb.S) * tb.Y * tb.T * 32 * sizeof(float);
+  return z_bytes + o_bytes;
+}
+
+int w2a_precompute_logits(w2a_ctx* ctx, void* stream) {
+  if (!ctx) return W2A_E_INVALID;
+  if (!ctx->have_features || !ctx->have_coefs || !ctx->tb.col_to_loc)
+    return fail(ctx, W2A_E_NOTREADY, "w2a_precompute_logits: call w2a_set_features, w2a_set_coefs and w2a_set_county_map first");
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  drop_tables(ctx);
+  w2a::Tables& tb = ctx->tb;
+  const int z_lines = (tb.Y + w2a::kZPerLine - 1) / w2a::kZPerLine;
+  const int64_t day_lines = static_cast<int64_t>(tb.Sw) * tb.P * z_lines;
+  if (day_lines * tb.T >= (int64_t{1} << 31))
+    return fail(ctx, W2A_E_INVALID, "w2a_precompute_logits: %lld table lines exceed the 31-bit line index",
+                static_cast<long long>(day_lines * tb.T));
+  const size_t z_bytes = static_cast<size_t>(day_lines) * tb.T * 128;
+  const size_t rows = static_cast<size_t>(tb.S) * tb.Y * tb.T;
+  const size_t o_bytes = rows * 32 * sizeof(float);
+  size_t free_b = 0, total_b = 0;
+  W2A_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  if (z_bytes + o_bytes + (size_t{1} << 30) > free_b)
+    return fail(ctx, W2A_E_NOMEM, "w2a_precompute_logits: the tables need %.2f GB, %.2f GB are free",
+                (z_bytes + o_bytes) * 1e-9, free_b * 1e-9);
+  W2A_CUDA(ctx, cudaMalloc(&ctx->table_scratch, z_bytes + o_bytes));
+  char* base = static_cast<char*>(ctx->table_scratch);
+  float4* z_all = reinterpret_cast<float4*>(base);
+  float* x32 = reinterpret_cast<float*>(base + z_bytes);
+  W2A_CUDA(ctx, cudaMemsetAsync(z_all, 0, z_bytes, st));  // columns without a county keep zero lines
+  tb.z_lines = z_lines;
+  tb.z_day_lines = static_cast<unsigned>(day_lines);
+  {
+    const int grid = static_cast<int>(std::min<size_t>((rows + 7) / 8, static_cast<size_t>(ctx->sm_count) * 16));
+    w2a::obs_rows_kernel<<<grid, 256, 0, st>>>(tb.x, x32, static_cast<unsigned>(rows));
+    ctx->launches++;
+  }
+  {
+    const int tasks = tb.Sw * ((tb.P + 7) / 8);
+    const unsigned gx = static_cast<unsigned>((tasks + w2a::kTableTaskWarps - 1) / w2a::kTableTaskWarps);
+    // blockIdx.y = day; at most 65 535 days per launch (T <= 255)
+    w2a::logit_all_kernel<<<dim3(gx, static_cast<unsigned>(tb.T)), 32 * w2a::kTableTaskWarps, 0, st>>>(tb, z_all, 0);
+    ctx->launches++;
+  }
+  W2A_CUDA(ctx, cudaGetLastError());
+  tb.z_all = z_all;
+  tb.x32 = x32;
   return W2A_OK;
 }
 
@@ -420,6 +500,8 @@ int w2a_host_envs_create(w2a_ctx* ctx, int64_t n) {
   W2A_CUDA(ctx, cudaMalloc(&h->idx, un * 5 * sizeof(int32_t)));
   W2A_CUDA(ctx, cudaMalloc(&h->mask, un));
   W2A_CUDA(ctx, cudaMemset(h->obs, 0, un * W2A_OBS_DIM * sizeof(float)));
+  h->noncanon.assign(un, 1);
+  h->n_noncanon = n;
   for (auto& s : h->streams) W2A_CUDA(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   return W2A_OK;
 }
@@ -436,6 +518,17 @@ int w2a_reset_host(w2a_ctx* ctx, const int32_t* loc, const int32_t* year, const 
   const int64_t n = h->n;
   uint2* sstat = plane_static(h->state);
   uint2* smut = plane_mut(h->state, n);
+  // an env is canonical when its coefficient column is its own county: known here from the host streams
+  {
+    const std::vector<int32_t>& map = ctx->col_to_loc_host;
+    for (int64_t i = 0; i < n; ++i) {
+      if (mask && !mask[i]) continue;
+      const int32_t c = coef_col[i];
+      const uint8_t non = !(c >= 0 && static_cast<size_t>(c) < map.size() && map[static_cast<size_t>(c)] == loc[i]);
+      h->n_noncanon += static_cast<int64_t>(non) - static_cast<int64_t>(h->noncanon[static_cast<size_t>(i)]);
+      h->noncanon[static_cast<size_t>(i)] = non;
+    }
+  }
   int ci = 0;
   for (int64_t c0 = 0; c0 < n; c0 += kHostChunk, ++ci) {
     const int64_t m = std::min(kHostChunk, n - c0);
@@ -476,8 +569,9 @@ int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward
   const int64_t n = h->n;
   uint2* sstat = plane_static(h->state);
   uint2* smut = plane_mut(h->state, n);
-  // one kernel variant for the whole batch, so that chunking never changes a result bit
-  const int variant = W2A_STEP_COOP;
+  // one kernel variant for the whole batch, so that chunking never changes a result bit: the tabulated
+  // logits when every env steps on its own county's column and the tables exist, else the cooperative kernel
+  const int variant = (ctx->tb.z_all && h->n_noncanon == 0) ? W2A_STEP_TABLE : W2A_STEP_COOP;
   if (h->packed) {
     const size_t un = static_cast<size_t>(n), obs_b = un * W2A_OBS_DIM * sizeof(float);
     cudaStream_t st = h->streams[0];

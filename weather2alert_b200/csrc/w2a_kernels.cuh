@@ -30,6 +30,7 @@ constexpr int kWStride = 64;   // float32 per coefficient record
 constexpr int kXSig = 24;      // record position of the significance code (0 = none)
 constexpr int kWOther = 56;    // first float of the non-table coefficients
 constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned kRecMask = 0xffffffu;  // static state plane, word y: coefficient record index; the year index sits above it
 // env.py:221 -- the reference divides by 152, not 153
 constexpr double kRewardScale = -1000.0 / 152.0;
 
@@ -45,26 +46,23 @@ struct Tables {
   // remaining_budget, bias
   const float* w;
   int S, Y, T, P, Sw;
-  // ---- the per-step logit table (step variant TABLE), all null / 0 until w2a_set_county_map ----
-  const int32_t* col_to_loc;  // [Sw] feature-store county of coefficient column `col`, -1 = none
-  // per (col, p): z_lines lines of 128 bytes; each line = the 6 agent coefficients (lag, streak,
+  const int32_t* col_to_loc;  // [Sw] feature-store county of coefficient column `col`, -1 = none (w2a_set_county_map)
+  // ---- whole-summer tables of step variant TABLE (w2a_precompute_logits), null / 0 before ----------
+  // z_all[t][col*P + p][z_lines] lines of 128 bytes; a line = the 6 agent coefficients (lag, streak,
   // remaining budget as (b, e) pairs; 24 bytes + 8 zero) followed by the (z_b, z_e) float64 table
-  // parts (gate and bias included) of 6 consecutive years for day t_cell: an env finds all it
-  // needs for its logits in ONE cache line
-  float4* z_tab;
+  // parts (gate and bias included) of 6 consecutive years on day t, for the county the column belongs
+  // to: an env finds all it needs for its logits in ONE cache line, whatever day it is on
+  const float4* z_all;
   int z_lines;                // ceil(Y / 6)
-  float* xobs_t;              // [S*Y, 32] float32 observation rows (slot order) of day t_cell
-  int* t_cell;                // the day the two tables were built for
-  unsigned long long magic_T, magic_Y;  // ceil(2^40 / d): exact n / d for n < 2^24, d < 2^16
+  unsigned z_day_lines;       // Sw * P * z_lines: lines per day
+  // x32[row][32]: the float32 observation row (slot order 0..28, significance as NaN / label) of
+  // day-row `row` of x: the row copy of _get_obs (env.py:187) is one 128-byte line per env
+  const float* x32;
 };
-
-__device__ __forceinline__ unsigned div_magic(unsigned n, unsigned long long magic) {
-  return static_cast<unsigned>((static_cast<unsigned long long>(n) * magic) >> 40);
-}
 
 struct StepArgs {
   Tables tb;
-  const uint2* st_static;  // x: row0 (24 bit) | n_days << 24 ; y: coefficient record index
+  const uint2* st_static;  // x: row0 (24 bit) | n_days << 24 ; y: coefficient record index (24 bit) | year index << 24
   uint2* st_mut;           // x: remaining budget (int32)      ; y: t | streak<<8 | win14<<16 | done<<30 | canonical<<31
   const void* action;
   float* obs;
@@ -91,6 +89,11 @@ struct ResetArgs {
 };
 
 // ---- helpers --------------------------------------------------------------------------
+// programmatic dependent launch: a step kernel lets the next launch on the stream get resident while it
+// drains, and itself waits for the previous launch (and its memory) before touching anything it wrote
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint2 ld_stream(const uint2* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(uint2* p, uint2 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
@@ -188,6 +191,8 @@ __device__ __forceinline__ Transition advance(uint2 sv, uint2& mv, int a) {
 template <int ADT>
 __global__ void __launch_bounds__(128) step_thread_kernel(const StepArgs p) {
   const int stride = gridDim.x * blockDim.x;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += stride) {
     const uint2 sv = ld_stream(p.st_static + e);
     uint2 mv = ld_stream(p.st_mut + e);
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(128) step_thread_kernel(const StepArgs p) {
     st_stream(p.st_mut + e, mv);
 
     const double* __restrict__ xr = p.tb.x + static_cast<size_t>(tr.row) * kXStride;
-    const float* __restrict__ wv = p.tb.w + static_cast<size_t>(sv.y) * kWStride;
+    const float* __restrict__ wv = p.tb.w + static_cast<size_t>(sv.y & kRecMask) * kWStride;
     float* ob = p.obs + static_cast<size_t>(e) * kObsDim;
     // bias first, then the 24 table features, then the three agent terms
     double zb = static_cast<double>(__ldg(wv + kWOther + 6)), ze = static_cast<double>(__ldg(wv + kWOther + 7));
@@ -334,6 +339,9 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigne
 __device__ __forceinline__ void bulk_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_store_wait_all() {  // the writes themselves are done, not only the reads
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, AHEAD > 4 ? 1 : W2A_COOP_MINB
       cur_tr = advance(sv, mv, a);
       const int e = (group << 5) + lane;
       if (e < p.n) st_stream(p.st_mut + e, mv);
-      cur_cv = sv.y;
+      cur_cv = sv.y & kRecMask;
 #pragma unroll
       for (int d = 0; d < PRE; ++d) {
         const unsigned rowd = __shfl_sync(kFull, cur_tr.row, 2 * d + row_g);
@@ -430,6 +438,8 @@ __global__ void __launch_bounds__(32 * kCoopWarps, AHEAD > 4 ? 1 : W2A_COOP_MINB
       }
     }
   };
+  pdl_launch_dependents();
+  pdl_wait();  // the previous launch on the stream wrote the state (and the actions) this one reads
   fetch_inputs(wg);
   open_group(wg);
   fetch_inputs(wg + warps_total);
@@ -534,35 +544,33 @@ __global__ void __launch_bounds__(32 * kCoopWarps, AHEAD > 4 ? 1 : W2A_COOP_MINB
     }
     __syncwarp();
   }
-  if (bulk_pending && lane == 0) bulk_store_wait_read();
+  if (bulk_pending && lane == 0) bulk_store_wait_all();
 }
 
 // =========================================================================================
-// step, variant TABLE: two launches per step for big, non-augmented env sets.
+// step, variant TABLE: one 128-byte record + one 128-byte observation row per env.
 //
-// The table part of both logits depends on (county, year, day, posterior sample) only.  With
-// more envs than such combinations (S*Y*P = 820 600 for the real shapes) it is cheaper to
-// evaluate ALL combinations of today once -- one CTA per county keeps that county's P
-// coefficient records in registers and its Y day-rows in shared memory, perfect locality, no
-// per-env gather of 512 bytes -- and to let every env pick its entry:
-//   logit_table_kernel   z_tab line (col*P + p, year / 6) = agent coefficients + (z_b, z_e) of six
-//                        years (gate and bias included), and xobs_t[s*Y + y][29] = the float32
-//                        observation row, for day t_cell
-//   step_table_kernel    per env: transition, z = its entry + agent terms, sigmoids, reward (one
-//                        gathered line); per warp: the 32 observation rows are copies of xobs_t
-//                        rows (one more gathered line per env), patched with the agent slots, and
-//                        leave through one bulk (TMA) store.
-// The day is taken from env 0; an env on another day, or whose coefficient column is not its
-// own county (augmentation, quirk Q6), computes its logits and row directly from the tables
-// (same arithmetic as the THREAD kernel), so the result never depends on the envs being in
-// lock step -- only the speed does.
+// The table part of both logits depends on (county, year, day, posterior sample) only -- never on
+// the agent -- so it is evaluated ONCE for the whole feature store when the tables are installed
+// (w2a_precompute_logits: the reference's per-key loop env.py:206-217 hoisted out of `step`):
+//   logit_all_kernel   z_all[t] line (col*P + p, year / 6) = agent coefficients + (z_b, z_e) of six
+//                      years (gate and bias included), for every day t of the summer -- a float64
+//                      GEMM per (county, day) on the FP64 tensor path (DMMA)
+//   obs_rows_kernel    x32[row][0..28] = the float32 observation row of every day-row
+//   step_table_kernel  per env: transition, z = its entry of ITS OWN day + agent terms, sigmoids,
+//                      reward (one gathered line); per warp: the 32 observation rows are copies of
+//                      x32 rows (one more gathered line per env), patched with the agent slots, and
+//                      leave through one bulk (TMA) store.
+// Every env looks its own day up, so envs need not march in lock step.  An env whose coefficient
+// column is not its own county (augmentation, quirk Q6: no `canonical` bit) computes its logits
+// directly from x / w (the THREAD kernel's arithmetic): results never depend on the variant.
 // =========================================================================================
 
 constexpr int kZPerLine = 6;     // (z_b, z_e) entries per 128-byte line, after the 32-byte head
 #ifndef W2A_TABLE_TASK_WARPS
-#define W2A_TABLE_TASK_WARPS 4  // B200 sweep: 2 and 4 warps per CTA equal, 8 is 6 % slower, 16 a third slower
+#define W2A_TABLE_TASK_WARPS 4
 #endif
-constexpr int kTableTaskWarps = W2A_TABLE_TASK_WARPS;  // warps (= tasks) per CTA of logit_table_kernel
+constexpr int kTableTaskWarps = W2A_TABLE_TASK_WARPS;  // warps (= tasks) per CTA of logit_all_kernel
 #ifndef W2A_TABLE_BUILD_MINBLOCKS
 #define W2A_TABLE_BUILD_MINBLOCKS 6  // x 4 warps = 24 warps/SM at 80 registers
 #endif
@@ -575,48 +583,20 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-// The table build is a small float64 GEMM per county -- Z[(p, head), y] = W[(p, head), 0..23] .
+// The logit table is a small float64 GEMM per (county, day) -- Z[(p, head), y] = W[(p, head), 0..23] .
 // X[y, 0..23]^T, plus the bias and (for z_e) the gate column -- so it runs on the FP64 tensor path:
-// one warp per task = (coefficient column, block of 8 posterior samples): 6 k-steps x 2 heads per
-// tile of 8 years of m8n8k4.  Operands come straight from the L2-resident tables; everything that
-// depends on the task index alone (coefficients, line heads) is requested before the first wait,
-// and the day-rows (which need the day and the county: one dependent round trip) of the first two
-// year tiles right after.  The leading tasks write the float32 observation rows instead.
+// one warp per task = (day, coefficient column, block of 8 posterior samples): 6 k-steps x 2 heads
+// per tile of 8 years of m8n8k4.  blockIdx.y = day.  Everything that depends on the task index alone
+// (coefficients, line heads) is requested before the first wait, the day-rows of the first two year
+// tiles right after.
 __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCKS)
-    logit_table_kernel(const Tables tb, const uint2* st_mut) {
+    logit_all_kernel(const Tables tb, float4* z_all, int t0) {
   const int lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int mtiles = (tb.P + 7) >> 3;
-  const int n_row_tasks = (tb.Sw + 3) >> 2;  // leading tasks: the observation rows of four columns each
-  const int task = blockIdx.x * kTableTaskWarps + (threadIdx.x >> 5) - n_row_tasks;
-  const unsigned t_word = __ldg(&st_mut[0].y);
-  if (task < 0) {
-    // ---- observation rows (slot order, float32) of day t for up to four coefficient columns ----
-    const int t = min(static_cast<int>(t_word & 0xffu), tb.T - 1);
-    if (task == -n_row_tasks && lane == 0) *tb.t_cell = t;
-    const int pos = lane < 23 ? lane : lane == 26 ? 23 : lane == 27 ? kXSig : -1;
-    for (int c = 0; c < 4; ++c) {
-      const int col = (task + n_row_tasks) * 4 + c;
-      if (col >= tb.Sw) break;
-      const int s = __ldg(tb.col_to_loc + col);
-      if (s < 0) continue;
-      const double* xrow = tb.x + (static_cast<size_t>(s) * tb.Y * tb.T + t) * kXStride + max(pos, 0);
-      for (int y0 = 0; y0 < tb.Y; y0 += 8) {
-        double v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          v[j] = y0 + j < tb.Y ? __ldg(xrow + static_cast<size_t>(y0 + j) * tb.T * kXStride) : 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float f = pos >= 0 ? static_cast<float>(v[j]) : 0.f;
-          if (lane == 27) f = sig_to_obs(f);
-          if (y0 + j < tb.Y) tb.xobs_t[static_cast<size_t>(s * tb.Y + y0 + j) * 32 + lane] = f;
-        }
-      }
-    }
-    return;
-  }
-  if (task >= tb.Sw * mtiles) return;
+  const int task = blockIdx.x * kTableTaskWarps + (threadIdx.x >> 5);
+  const int t = t0 + static_cast<int>(blockIdx.y);
+  if (task >= tb.Sw * mtiles || t >= tb.T) return;
   const int col = task / mtiles, mt = task - col * mtiles;
   const int s = __ldg(tb.col_to_loc + col);
   const int p = mt * 8 + gid;  // this lane's row of A and C
@@ -627,9 +607,8 @@ __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCK
   for (int ks = 0; ks < 6; ++ks) wv[ks] = __ldg(wrec + 4 * ks + tig);
   const float2 bias = __ldg(wrec + 31);
   float4 h = __ldg(reinterpret_cast<const float4*>(wrec) + 14 + (tig & 1));  // lag, streak | remaining budget, bias
-  if (s < 0) return;
-  const int t = min(static_cast<int>(t_word & 0xffu), tb.T - 1);
-  float4* rec = tb.z_tab + static_cast<size_t>(col * tb.P + p) * (tb.z_lines * 8);
+  if (s < 0) return;  // a column without a county in the store: its lines stay zero, no env is canonical on it
+  float4* rec = z_all + (static_cast<size_t>(t) * tb.z_day_lines + static_cast<size_t>(col * tb.P + p) * tb.z_lines) * 8;
   const double* xday = tb.x + (static_cast<size_t>(s) * tb.Y * tb.T + t) * kXStride;
   const size_t ystride = static_cast<size_t>(tb.T) * kXStride;
   // year tiles of 8: B fragments x[y0 + gid][4*ks + tig] and, for this lane's two columns of C,
@@ -676,6 +655,19 @@ __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCK
   }
 }
 
+// float32 observation rows (slot order) of every day-row: one warp per row, lane = slot.  Slots 23..25
+// and 28 (agent slots, patched by the step kernel) and the pad lanes 29..31 are zero.
+__global__ void __launch_bounds__(256) obs_rows_kernel(const double* __restrict__ x, float* __restrict__ x32, unsigned rows) {
+  const int lane = threadIdx.x & 31;
+  const unsigned warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int pos = lane < 23 ? lane : lane == 26 ? 23 : lane == 27 ? kXSig : -1;
+  for (unsigned r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_total) {
+    float f = pos >= 0 ? static_cast<float>(__ldg(x + static_cast<size_t>(r) * kXStride + pos)) : 0.f;
+    if (lane == 27) f = sig_to_obs(f);
+    x32[static_cast<size_t>(r) * 32 + lane] = f;
+  }
+}
+
 struct __align__(128) TableScratchWarp {
   float obs[32 * kObsDim];
 };
@@ -691,6 +683,17 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #ifndef W2A_TABLE_MINBLOCKS
 #define W2A_TABLE_MINBLOCKS 8  // x 4 warps = 32 warps/SM at 64 registers
 #endif
+#ifndef W2A_TABLE_PREFETCH
+#define W2A_TABLE_PREFETCH 0  // 1: every env asks L2 for tomorrow's record line; 2: and tomorrow's observation row
+#endif
+#ifndef W2A_Z_POLICY
+#define W2A_Z_POLICY 0  // L2 policy of the record gather: 0 default, 1 evict_last
+#endif
+#ifndef W2A_KNOCK
+#define W2A_KNOCK 0  // timing studies only (results become wrong): 1 no observation store, 2 record gather from line 0,
+#endif               // 4 row gather from row 0, 8 no reward / flag outputs
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int ADT>
 __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_table_kernel(const StepArgs p) {
@@ -701,16 +704,19 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
   const int g = lane >> 3;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int n_groups = (p.n + 31) >> 5;
-  const int t_table = *p.tb.t_cell;
+#if W2A_Z_POLICY == 1
   const unsigned long long keep = l2_policy_evict_last();
+#endif
   const unsigned long long stream_out = l2_policy_evict_first();
   const bool obs_aligned = (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
-  const float4* const xobs_lane = reinterpret_cast<const float4*>(p.tb.xobs_t) + q;
+  const float4* const x32_lane = reinterpret_cast<const float4*>(p.tb.x32) + q;
   float* const my_row = stage + lane * kObsDim;
   bool bulk_pending = false;
 
+  pdl_launch_dependents();
   int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wg >= n_groups) return;
+  pdl_wait();  // the previous launch on the stream wrote the state (and the actions) this one reads
   // the next group's state and action are in flight while this group's gathers are waited for
   uint2 sv_n, mv_n;
   int a_n;
@@ -728,20 +734,23 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     const uint2 sv = sv_n;
     uint2 mv = mv_n;
     const int a = a_n;
-    const int t_before = mv.y & 0xff;
-    const bool canon = (mv.y >> 31) != 0;
+    const unsigned t_before = mv.y & 0xffu;
+    const bool fast = (mv.y >> 31) != 0;  // canonical: the env's column is its own county -> its logits are tabulated
     const Transition tr = advance(sv, mv, a);
-    const unsigned cv = sv.y;
-    const unsigned sy = div_magic(sv.x & 0xffffffu, p.tb.magic_T);
-    const unsigned yr = sy - div_magic(sy, p.tb.magic_Y) * static_cast<unsigned>(p.tb.Y);
-    const bool fast = canon && t_before == t_table;
-    const unsigned fast_mask = __ballot_sync(kFull, fast);
+    const unsigned cv = sv.y & kRecMask;
+    const unsigned yr = sv.y >> 24;
     // ---- every gather of the group is issued before anything waits on one ---------------------------
-    // (loads are unconditional -- an env off the fast path reads record 0 and ignores it -- so that no
+    // (loads are unconditional -- an env off the fast path reads line 0 and ignores it -- so that no
     // select sits between a load and the next one)
     const unsigned zl = (yr * 10923u) >> 16;  // year / 6 (exact below 2^14)
-    const float4* zrec = p.tb.z_tab + (static_cast<size_t>(fast ? cv : 0u) * p.tb.z_lines + (fast ? zl : 0u)) * 8;
+    const unsigned line =
+        (fast && !(W2A_KNOCK & 2)) ? t_before * p.tb.z_day_lines + cv * static_cast<unsigned>(p.tb.z_lines) + zl : 0u;
+    const float4* zrec = p.tb.z_all + static_cast<size_t>(line) * 8;
+#if W2A_Z_POLICY == 1
     const float4 o0 = ldg_keep(zrec, keep);
+#else
+    const float4 o0 = __ldg(zrec);
+#endif
     const float2 o1 = __ldg(reinterpret_cast<const float2*>(zrec + 1));
     const double2 z = __ldg(reinterpret_cast<const double2*>(zrec + 2) + (fast ? yr - zl * kZPerLine : 0u));
     float4 rows[W2A_TABLE_ROWS];  // observation rows: 8 lanes copy one float32 row, four neighbouring envs per round
@@ -749,28 +758,34 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
 #pragma unroll
       for (int it = 0; it < W2A_TABLE_ROWS; ++it) {
         const int j = 4 * (first + it) + g;
-        const unsigned syj = __shfl_sync(kFull, sy, j);
-        rows[it] = __ldg(xobs_lane + static_cast<size_t>(((fast_mask >> j) & 1u) ? syj : 0u) * 8);
+        const unsigned rowj = (W2A_KNOCK & 4) ? 0u : __shfl_sync(kFull, tr.row, j);
+        rows[it] = __ldg(x32_lane + static_cast<size_t>(rowj) * 8);
       }
     };
     auto stage_rows = [&](int first) {
 #pragma unroll
       for (int it = 0; it < W2A_TABLE_ROWS; ++it) {
         const int j = 4 * (first + it) + g;
-        if ((fast_mask >> j) & 1u) {
-          float* st = stage + j * kObsDim + 4 * q;
-          st[0] = rows[it].x;
-          if (q < 7) {
-            st[1] = rows[it].y;
-            st[2] = rows[it].z;
-            st[3] = rows[it].w;
-          }
+        float* st = stage + j * kObsDim + 4 * q;
+        st[0] = rows[it].x;
+        if (q < 7) {
+          st[1] = rows[it].y;
+          st[2] = rows[it].z;
+          st[3] = rows[it].w;
         }
       }
     };
     load_rows(0);
     if (valid) st_stream(p.st_mut + e, mv);
     if (wg + warps_total < n_groups) fetch(wg + warps_total);
+#if W2A_TABLE_PREFETCH >= 1
+    if (fast && !tr.done) {  // tomorrow's line of this env: a day further in z_all
+      prefetch_l2(zrec + static_cast<size_t>(p.tb.z_day_lines) * 8);
+#if W2A_TABLE_PREFETCH >= 2
+      prefetch_l2(p.tb.x32 + static_cast<size_t>(tr.row + 1) * 32);
+#endif
+    }
+#endif
     const bool write_obs = valid && !tr.done;
     const unsigned wmask = __ballot_sync(kFull, write_obs);
     if (bulk_pending) {  // the previous group's bulk store must have finished reading the staging buffer
@@ -781,7 +796,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     // ---- logits -------------------------------------------------------------------------------
     double zb = z.x, ze = z.y;
     float lag_b = o0.x, lag_e = o0.y, streak_b = o0.z, streak_e = o0.w, rem_b = o1.x, rem_e = o1.y;
-    if (!fast) {  // off-day or non-canonical env: straight from the tables, row staged by its own thread
+    if (!fast) {  // non-canonical env (similar-county column, Q6): straight from the tables
       const double* xr = p.tb.x + static_cast<size_t>(tr.row) * kXStride;
       const float* wv = p.tb.w + static_cast<size_t>(cv) * kWStride;
       zb = __ldg(xr + 25) * static_cast<double>(__ldg(wv + 50));
@@ -790,9 +805,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
         const double x = __ldg(xr + u);
         zb = fma(x, static_cast<double>(__ldg(wv + 2 * u)), zb);
         ze = fma(x, static_cast<double>(__ldg(wv + 2 * u + 1)), ze);
-        my_row[slot_of_feature(u)] = static_cast<float>(x);
       }
-      my_row[27] = sig_to_obs(static_cast<float>(__ldg(xr + kXSig)));
       zb += static_cast<double>(__ldg(wv + kWOther + 6));
       ze += static_cast<double>(__ldg(wv + kWOther + 7));
       lag_b = __ldg(wv + kWOther); lag_e = __ldg(wv + kWOther + 1);
@@ -809,13 +822,14 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
       zb = fma(f_rem, static_cast<double>(rem_b), zb);
       ze = fma(f_rem, static_cast<double>(rem_e), ze);
     }
-    if (valid) {
+    if (valid && !(W2A_KNOCK & 8)) {
       __stcs(p.reward + e, step_reward(zb, ze, tr.act));
       p.terminated[e] = static_cast<uint8_t>(tr.done);
       if (p.remaining) __stcs(p.remaining + e, tr.rem);
       if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
+    } else if (W2A_KNOCK & 8) {
+      if (step_reward(zb, ze, tr.act) == 123.f) p.reward[e] = 0.f;  // keeps the arithmetic alive
     }
-    __syncwarp();
 #pragma unroll
     for (int first = 0; first < 8; first += W2A_TABLE_ROWS) {
       if (first > 0) load_rows(first);
@@ -829,7 +843,9 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     fence_proxy_async_smem();
     __syncwarp();
     float* const ob = p.obs + static_cast<size_t>(base) * kObsDim;
-    if (wmask == kFull && obs_aligned) {
+    if (W2A_KNOCK & 1) {
+      if (stage[lane] == 123.f) ob[lane] = 0.f;
+    } else if (wmask == kFull && obs_aligned) {
       if (lane == 0) bulk_store(ob, stage, kObsBlockBytes, stream_out);
       bulk_pending = true;
     } else if (wmask != 0u) {
@@ -840,7 +856,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     }
     __syncwarp();
   }
-  if (bulk_pending && lane == 0) bulk_store_wait_read();
+  if (bulk_pending && lane == 0) bulk_store_wait_all();
 }
 
 // =========================================================================================
@@ -874,7 +890,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
     const int colv = __ldcs(p.coef_col + ec);
     const bool canon = p.tb.col_to_loc != nullptr && __ldg(p.tb.col_to_loc + colv) == __ldcs(p.loc + ec);
     if (take) {
-      st_stream(p.st_static + e, make_uint2(row0 | (nd << 24), cv));
+      st_stream(p.st_static + e, make_uint2(row0 | (nd << 24), cv | (static_cast<unsigned>(__ldcs(p.year + ec)) << 24)));
       st_stream(p.st_mut + e, make_uint2(static_cast<unsigned>(budget), canon ? 0x80000000u : 0u));  // t = streak = win = 0
       if (p.remaining) p.remaining[e] = budget;
     }
@@ -977,7 +993,7 @@ enum StatIndex {
 template <bool POLICY>
 __global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const RolloutArgs p) {
   __shared__ double s_stats[kNumStats];
-  __shared__ unsigned char s_days[4][4][24];  // [warp][group][chunk]: issued-alert bits of the episode so far
+  __shared__ unsigned char s_days[4][4][32];  // [warp][group][chunk of 8 days]: issued-alert bits of the episode so far (T <= 255)
   if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -996,7 +1012,7 @@ __global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const Roll
     const bool valid = e < p.n;
     const int ec = valid ? e : p.n - 1;
     const uint2 sv = __ldg(p.st_static + ec);
-    const uint2 mv = __ldg(p.st_mut + ec);
+    const uint2 mv = ld_stream(p.st_mut + ec);  // written later in this launch: not through the read-only path
     const int n_days = sv.x >> 24;
     const unsigned row0 = sv.x & 0xffffffu;
     int rem = static_cast<int>(mv.x);
@@ -1008,7 +1024,7 @@ __global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const Roll
     const bool whole_episode = t == 0;
 
     // coefficient record -> float64 registers, once per episode
-    const float4* wr = reinterpret_cast<const float4*>(p.tb.w + static_cast<size_t>(sv.y) * kWStride);
+    const float4* wr = reinterpret_cast<const float4*>(p.tb.w + static_cast<size_t>(sv.y & kRecMask) * kWStride);
     const float4 wa4 = __ldg(wr + q), wb4 = __ldg(wr + 8 + q);
     const float4 o0 = __ldg(wr + 14), o1 = __ldg(wr + 15);  // (b,e) of lag1, streak | remaining, bias
     const double wab0 = wa4.x, wae0 = wa4.y, wab1 = wa4.z, wae1 = wa4.w;
