@@ -72,6 +72,78 @@ def test_vector_env_state_dict_replay(golden):
             assert torch.equal(x.view(torch.uint8), y.view(torch.uint8))
 
 
+def test_state_dict_resume_crosses_an_autoreset_with_reset_options(golden):
+    """a FRESH env that loads the checkpoint must autoreset with the options of the original
+    `reset` (similar-county augmentation, budget sampling) and show the same infos and statistics."""
+    from weather2alert_b200 import HeatAlertVectorEnv
+
+    n = 96
+    kw = dict(weights=golden.weights("std"), store=golden.store(), track_stats=True)
+    opts = dict(similar_climate_counties=True, budget=7, sample_budget=True, sample_budget_type="centered")
+    env = HeatAlertVectorEnv(n, seed=5, **kw)
+    env.reset(options=opts)
+    acts = [torch.from_numpy(np.random.default_rng(i).random(n) < 0.5).cuda() for i in range(200)]
+    for a in acts[:100]:
+        env.step(a)
+    snap = env.state_dict()
+
+    def run(e):
+        out = []
+        for a in acts[100:]:  # crosses the end of the 150-day and of the 153-day summers
+            o, r, t, _, info = e.step(a)
+            out.append((o.clone(), r.clone(), t.clone(), info["remaining_budget"].clone(), info["at_budget"].clone(),
+                        info["location_index"].clone()))
+        return out, e.stats.totals.clone()
+
+    first, tot1 = run(env)
+    fresh = HeatAlertVectorEnv(n, seed=999, **kw)  # different seed, default options: everything comes from the checkpoint
+    fresh.load_state_dict(snap)
+    assert fresh._variant() == env._variant()
+    i0 = fresh._infos()
+    assert torch.equal(i0["remaining_budget"], snap["rem"]) and torch.equal(i0["at_budget"], snap["atb"])
+    again, tot2 = run(fresh)
+    for f, g in zip(first, again):
+        for x, y in zip(f, g):
+            assert torch.equal(x.view(torch.uint8), y.view(torch.uint8))
+    assert torch.equal(tot1, tot2)
+
+
+def test_autoreset_infos_and_masked_draws_stay_unsorted(golden):
+    """SAME_STEP autoreset keeps the terminal step's info in `final_info`; a masked autoreset (ragged summers) does
+    not sort its draws (sorting a subset would tie slots to county ranges), a full reset does."""
+    from weather2alert_b200 import HeatAlertVectorEnv
+
+    store, weights = golden.store(), golden.weights("std")
+    n = 400
+    env = HeatAlertVectorEnv(n, weights=weights, store=store, seed=3, budget=3)
+    env.reset()
+    key = lambda d: ((d["loc"].long() * 1000 + d["coef_col"]) * 1000 + d["coef_idx"]) * 100 + d["year"]  # noqa: E731
+    k0 = key(env._idx)
+    assert bool((k0[1:] >= k0[:-1]).all())  # the full reset is sorted
+    saw_partial = False
+    rng = np.random.default_rng(0)
+    for i in range(160):
+        prev_rem = env._rem.clone()
+        act = torch.from_numpy(rng.random(n) < 0.2).cuda()
+        obs, rew, term, _, info = env.step(act)
+        if bool(term.any()):
+            fi = info["final_info"]
+            assert torch.equal(fi["_mask"], term)
+            # the terminal step's remaining budget (post-action) is what final_info holds; infos show the new episode
+            assert bool((fi["remaining_budget"][term] <= prev_rem[term]).all())
+            assert bool((info["remaining_budget"][term] == 3).all()) and not bool(info["at_budget"][term].any())
+            if not bool(term.all()):
+                saw_partial = True
+                k = key(env._idx)
+                assert not bool((k[1:] >= k[:-1]).all())  # raw i.i.d. draws
+            ep = info["episode_index"].numpy()
+            lo, yr = env._ep_loc.cpu().numpy(), env._ep_year.cpu().numpy()
+            assert ep[0] == f"{store.fips[lo[0]]}_{store.years[yr[0]]}"
+        else:
+            assert "final_info" not in info
+    assert saw_partial
+
+
 def test_million_envs_properties(big_core):
     """BASELINE configs[2] size (2**20 envs): the two step variants agree, the launch is
     deterministic, halves equal the whole (sharding), and the budget invariants hold."""
@@ -160,8 +232,9 @@ def test_sort_episodes_is_a_permutation_of_the_same_draws(golden):
     from weather2alert_b200 import HeatAlertVectorEnv
 
     kw = dict(weights=golden.weights("std"), store=golden.store(), seed=9, similar_climate_counties=True)
-    a = HeatAlertVectorEnv(500, **kw)
-    b = HeatAlertVectorEnv(500, sort_episodes=True, **kw)
+    a = HeatAlertVectorEnv(500, sort_episodes=False, **kw)
+    b = HeatAlertVectorEnv(500, **kw)  # the default for device-sampled resets of the whole batch
+    assert b.sort_episodes and not a.sort_episodes
     a.reset()
     b.reset()
     ka = torch.stack([a._idx[k] for k in ("loc", "coef_col", "coef_idx", "year")], 1).cpu().numpy()
@@ -221,8 +294,13 @@ def test_reference_rng_reset_equals_independent_single_envs(golden):
         o, inf = e.reset(seed=seed + i, similar_climate_counties=True, sample_budget=True, sample_budget_type="centered")
         np.testing.assert_array_equal(obs[i].cpu().numpy().view(np.int32), o.view(np.int32))
         assert inf["remaining_budget"] == int(info["remaining_budget"][i])
-        assert weights.fips_list.index(str(inf["location"])) == int(info["location_index"][i])
+        # the reference's info (env.py:228-236): location_index is the coefficient column (Q6: the index inside
+        # the similar-county list), location the similar county, episode_index the ORIGINAL county's episode
+        assert inf["location_index"] == int(info["location_index"][i])
+        assert weights.fips_list.index(str(inf["location"])) == int(info["location_list_index"][i])
+        assert str(info["location"][i]) == str(inf["location"]) and info["episode_index"][i] == inf["episode_index"]
         singles.append(e)
+    assert len(info["location"]) == n and info["feature_names"] == singles[0].feat_names
     rng = np.random.default_rng(0)
     for _ in range(25):
         a = rng.integers(0, 2, n)

@@ -8,6 +8,7 @@ try:  # pragma: no cover - depends on the image
     from gymnasium import spaces
 
     Env = _gym.Env
+    VectorEnv = _gym.vector.VectorEnv
     HAVE_GYMNASIUM = True
 except ImportError:  # the build image has no gymnasium wheel
     HAVE_GYMNASIUM = False
@@ -20,6 +21,14 @@ except ImportError:  # the build image has no gymnasium wheel
 
         def close(self):
             pass
+
+    class VectorEnv:  # noqa: D401 - the attributes gymnasium.vector.VectorEnv declares, nothing more
+        metadata: dict = {}
+        num_envs: int
+        closed: bool = False
+
+        def close(self, **kwargs):
+            self.closed = True
 
     class _Spaces:
         class Box:

@@ -60,7 +60,8 @@ class HeatAlertEnv(Env):
         self.action_space = spaces.Discrete(2)  # alert or no alert
         self.feat_names = list(schema.OBS_NAMES)
 
-        self.core = HeatAlertCore(self.store, self.weights, device)  # raises without GPU / built extension
+        # raises without GPU / built extension; a batch of one does not pay for the whole-summer tables (3 GB)
+        self.core = HeatAlertCore(self.store, self.weights, device, precompute=False)
         self.core.host_envs_create(1)
         self._obs = np.zeros((1, schema.OBS_DIM), np.float32)
         self._reward = np.zeros(1, np.float32)

@@ -15,9 +15,18 @@ reference, whose own resets seed one PCG64 per env).
 
 Autoreset is SAME_STEP: an env that terminates is reset inside the same `step` call (the
 returned observation is the first one of its next episode; the reference's terminal
-observation is just the previous one, quirk Q2).  Termination is ``t >= n_days - 1``,
+observation is just the previous one, quirk Q2); the terminal step's `remaining_budget` /
+`at_budget` are kept in ``infos["final_info"]``.  Termination is ``t >= n_days - 1``,
 a function of the sampled episode only, so when all summers have the same length the
 host knows the schedule and autoreset needs no device->host synchronisation.
+
+`infos` carries, per env: `remaining_budget`, `at_budget`, `location_index` (the reference's
+`info["location_index"]`, env.py:117,121,234: the coefficient column -- the index inside the
+similar-county list when augmenting), `location_list_index` (index of `info["location"]` in
+`fips_list`) as device tensors, and `episode_index` / `location` as lazily formatted string
+sequences (env.py:156,228-236; formatting them synchronises with the device).
+
+Subclasses `gymnasium.vector.VectorEnv` when gymnasium is importable (`_gym.HAVE_GYMNASIUM`).
 """
 from __future__ import annotations
 
@@ -25,13 +34,38 @@ import numpy as np
 import torch
 
 from . import _lib, schema
-from ._gym import spaces
+from ._gym import VectorEnv, spaces
 from .core import HeatAlertCore
 from .sampling import EpisodeSampler
 from .store import FeatureStore, RewardWeights
 
 
-class HeatAlertVectorEnv:
+class LazyStrings:
+    """Per-env strings of `infos` (`episode_index`, `location`; env.py:156,228-236), formatted on the host only
+    when somebody looks: indexing, iterating or `numpy()` copies the index tensors back (one synchronisation)."""
+
+    def __init__(self, n, make):
+        self._n, self._make, self._cache = n, make, None
+
+    def numpy(self) -> np.ndarray:
+        if self._cache is None:
+            self._cache = self._make()
+        return self._cache
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        return self.numpy()[i]
+
+    def __iter__(self):
+        return iter(self.numpy())
+
+    def __repr__(self):
+        return f"LazyStrings(n={self._n})"
+
+
+class HeatAlertVectorEnv(VectorEnv):
     metadata = {"autoreset_mode": "same_step"}
 
     def __init__(
@@ -50,7 +84,7 @@ class HeatAlertVectorEnv:
         core: HeatAlertCore | None = None,
         step_variant: int = _lib.STEP_AUTO,
         track_stats: bool = False,
-        sort_episodes: bool = False,
+        sort_episodes: bool | None = None,
     ):
         if core is None:
             if store is None or not isinstance(weights, RewardWeights):
@@ -69,8 +103,12 @@ class HeatAlertVectorEnv:
         self.step_variant = step_variant
         # Assign the sampled episodes to env slots in (county, coefficient column, sample, year)
         # order.  The draws are i.i.d., so which slot gets which episode is immaterial, but
-        # neighbouring envs then share table lines (profiles/r01: +8 % per step, +35 % per rollout).
-        self.sort_episodes = sort_episodes
+        # neighbouring envs then share table lines (+20..25 % per step, +35 % per rollout on a B200).
+        # Default (None): on, for device-sampled resets of the WHOLE batch only -- caller-supplied
+        # streams (`index_streams`, `reference_rng`) fix the slot order, and a masked autoreset (ragged
+        # summers) keeps its draws unsorted, because sorting a subset would tie slots to county ranges
+        # and over-sample short-summer counties.
+        self.sort_episodes = True if sort_episodes is None else bool(sort_episodes)
         self.sampler = EpisodeSampler(self.store, self.weights, years)
         self.fips_list = self.sampler.fips_list
         self.single_observation_space = spaces.Box(-np.inf, np.inf, (schema.OBS_DIM,), np.float32)
@@ -117,7 +155,13 @@ class HeatAlertVectorEnv:
 
             self.stats = RolloutStats(n, dev)
         self._idx = {}        # index streams of the most recent draw (device int32)
-        self._list_idx = torch.zeros(n, dtype=torch.int32, device=dev)  # county (fips_list index) per env
+        # per env, for `infos`: the episode (store county, store year), the coefficient column, and the
+        # fips_list index of the county reported as info["location"]
+        self._ep_loc = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._ep_year = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._coef_col = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._list_idx = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._final_info = None
         self._term_at = None  # device int64[n]: step number at which each env terminates
         self._step_no = 0
         self._next_term = None
@@ -127,8 +171,9 @@ class HeatAlertVectorEnv:
     def _randint(self, high, n):
         return torch.randint(0, int(high), (n,), generator=self._gen, device=self.device)
 
-    def _draw(self):
-        """Index streams for all N envs as device int32 tensors."""
+    def _draw(self, sort: bool = True):
+        """Index streams for all N envs as device int32 tensors (`list_idx`: the county reported as
+        info["location"], as fips_list index)."""
         n, dev, o = self.num_envs, self.device, self._reset_opts
         sp = self.sampler
         if "index_streams" in o:
@@ -193,12 +238,15 @@ class HeatAlertVectorEnv:
             no_similar = n_c <= 0
             u = torch.rand(n, generator=self._gen, device=dev, dtype=torch.float64)
             coef_col = torch.minimum((u * n_c).long(), n_c - 1)
-            if augment == "intended":  # NOT the reference: the episode moves to the drawn similar county
-                list_idx = self._similar_members[self._similar_start[list_idx] + coef_col.clamp(min=0)]
+            # env.py:118: the drawn similar county is what info["location"] reports ...
+            info_idx = self._similar_members[self._similar_start[list_idx] + coef_col.clamp(min=0)]
+            if augment == "intended":  # NOT the reference: ... and the episode moves there as well
+                list_idx = info_idx
                 coef_col = list_idx
                 loc = self._list_to_data[list_idx]
         else:
             coef_col = list_idx  # env.py:121
+            info_idx = list_idx
         year = self._valid_year_idx[self._randint(len(sp.valid_years), n)]  # env.py:125
         coef_idx = self._randint(sp.n_samples, n)  # env.py:160
         if not self._all_episodes_exist or (augment and not self._augment_safe):
@@ -209,7 +257,8 @@ class HeatAlertVectorEnv:
             if bool(bad.any()):  # the reference raises KeyError at env.py:127 / datautils.py:123
                 b = int(torch.nonzero(bad)[0])
                 raise KeyError((sp.fips_list[int(list_idx[b])], int(year[b])))
-        if self.sort_episodes:
+        list_idx = info_idx
+        if self.sort_episodes and sort:
             key = ((loc * self.core.Sw + coef_col) * sp.n_samples + coef_idx) * self.core.Y + year
             order = torch.argsort(key)
             loc, year, coef_col, coef_idx, list_idx = (v[order] for v in (loc, year, coef_col, coef_idx, list_idx))
@@ -259,15 +308,20 @@ class HeatAlertVectorEnv:
         return self._obs, self._infos()
 
     def _reset_subset(self, mask):
-        s = self._draw()
+        s = self._draw(sort=mask is None)
         self._idx = s
         self.core.reset(self._state, self._obs, s["loc"], s["year"], s["coef_col"], s["coef_idx"],
                         budget=s.get("budget"), mask=mask, remaining=self._rem)
         if mask is None:
-            self._list_idx = s["list_idx"]
+            self._ep_loc, self._ep_year, self._coef_col, self._list_idx = s["loc"], s["year"], s["coef_col"], s["list_idx"]
             self._atb.zero_()
         else:
-            self._list_idx = torch.where(mask.bool(), s["list_idx"], self._list_idx)
+            m = mask.bool()
+            self._ep_loc = torch.where(m, s["loc"], self._ep_loc)
+            self._ep_year = torch.where(m, s["year"], self._ep_year)
+            self._coef_col = torch.where(m, s["coef_col"], self._coef_col)
+            self._list_idx = torch.where(m, s["list_idx"], self._list_idx)
+            self._atb &= ~m
         if self._uniform_days is not None:
             if mask is None:  # lockstep: the host knows the whole schedule
                 self._term_at = None
@@ -311,7 +365,11 @@ class HeatAlertVectorEnv:
         if self.stats is not None:
             self.stats.update(actions, self._reward, self._term, self._atb)
         self._step_no += 1
+        self._final_info = None
         if self.autoreset and self._step_no >= self._next_term:
+            # SAME_STEP autoreset overwrites the info tensors of the envs it resets: keep the terminal step's
+            self._final_info = {"remaining_budget": self._rem.clone(), "at_budget": self._atb.clone(),
+                                "_mask": self._term.clone()}
             if self._term_at is None:
                 self._reset_subset(None)
             else:
@@ -388,27 +446,64 @@ class HeatAlertVectorEnv:
         return GraphedRollout(self, policy, steps, reset_at_end)
 
     def _infos(self):
-        return {"remaining_budget": self._rem, "at_budget": self._atb, "location_index": self._list_idx}
+        loc, year, lidx = self._ep_loc, self._ep_year, self._list_idx
+        fips, years, flist = self.store.fips, self.store.years, self.fips_list
+
+        def episode_index():  # env.py:156: ORIGINAL location (whose weather is played, Q7) + "_" + year
+            lo, yr = loc.cpu().numpy(), year.cpu().numpy()
+            return np.array([f"{fips[a]}_{years[b]}" for a, b in zip(lo, yr)], dtype=object)
+
+        def location():  # env.py:118,120: the similar county when augmenting, else the county itself
+            return np.array([flist[i] for i in lidx.cpu().numpy()], dtype=object)
+
+        infos = {"remaining_budget": self._rem, "at_budget": self._atb,
+                 "location_index": self._coef_col,       # env.py:117,121,234 (Q6: index in the similar list)
+                 "location_list_index": self._list_idx,  # info["location"] as fips_list index
+                 "episode_index": LazyStrings(self.num_envs, episode_index),
+                 "location": LazyStrings(self.num_envs, location),
+                 "feature_names": self.feature_names}
+        if self._final_info is not None:
+            infos["final_info"] = self._final_info
+        return infos
 
     # ---- checkpoint / resume ----------------------------------------------------------------------
     def state_dict(self):
-        return {"state": self._state.clone(), "obs": self._obs.clone(), "step_no": self._step_no,
-                "term_at": None if self._term_at is None else self._term_at.clone(),
-                "next_term": self._next_term, "list_idx": self._list_idx.clone(),
-                "gen": self._gen.get_state(), "host_rng": self._host_rng.bit_generator.state}
+        """Everything a fresh env (same tables, same constructor arguments) needs to continue exactly where this
+        one is: device state, observations and info tensors, the autoreset schedule, both RNGs, the options of
+        the last `reset` (they drive every later autoreset) and the rollout statistics."""
+        opts = {k: v for k, v in self._reset_opts.items()}
+        sd = {"state": self._state.clone(), "obs": self._obs.clone(), "rem": self._rem.clone(), "atb": self._atb.clone(),
+              "step_no": self._step_no, "term_at": None if self._term_at is None else self._term_at.clone(),
+              "next_term": self._next_term, "canonical": self._canonical, "reset_opts": opts,
+              "ep_loc": self._ep_loc.clone(), "ep_year": self._ep_year.clone(), "coef_col": self._coef_col.clone(),
+              "list_idx": self._list_idx.clone(),
+              "gen": self._gen.get_state(), "host_rng": self._host_rng.bit_generator.state}
+        if self.stats is not None:
+            sd["stats"] = {"totals": self.stats.totals.clone(), "ep_return": self.stats.ep_return.clone()}
+        return sd
 
     def load_state_dict(self, sd):
         self._state.copy_(sd["state"])
         self._obs.copy_(sd["obs"])
+        self._rem.copy_(sd["rem"])
+        self._atb.copy_(sd["atb"])
         self._step_no = int(sd["step_no"])
         self._term_at = None if sd["term_at"] is None else sd["term_at"].clone()
         self._next_term = sd["next_term"]
-        self._list_idx = sd["list_idx"].clone()
+        self._canonical = bool(sd["canonical"])
+        self._reset_opts = dict(sd["reset_opts"])
+        self._ep_loc, self._ep_year = sd["ep_loc"].clone(), sd["ep_year"].clone()
+        self._coef_col, self._list_idx = sd["coef_col"].clone(), sd["list_idx"].clone()
         self._gen.set_state(sd["gen"])
         self._host_rng.bit_generator.state = sd["host_rng"]
+        self._final_info = None
+        if self.stats is not None and "stats" in sd:
+            self.stats.totals.copy_(sd["stats"]["totals"])
+            self.stats.ep_return.copy_(sd["stats"]["ep_return"])
 
-    def close(self):
+    def close(self, **kwargs):
         self.core = None
+        self.closed = True
 
 
 class GraphedRollout:
@@ -436,12 +531,17 @@ class GraphedRollout:
                 env._idx = s
                 env.core.reset(env._state, env._obs, s["loc"], s["year"], s["coef_col"], s["coef_idx"],
                                budget=s.get("budget"), remaining=env._rem)
-                env._list_idx.copy_(s["list_idx"])
+                for dst, key in ((env._ep_loc, "loc"), (env._ep_year, "year"), (env._coef_col, "coef_col"),
+                                 (env._list_idx, "list_idx")):
+                    dst.copy_(s[key])
                 env._atb.zero_()
 
         # warm up on a side stream (lazy initialisation of torch kernels and of the launch tables), on
         # a copy of the env state so that the capture starts from where the env is now
-        snap = (env._state.clone(), env._obs.clone(), env._gen.get_state(), env._list_idx.clone())
+        info_t = ("_ep_loc", "_ep_year", "_coef_col", "_list_idx")
+        for name in info_t:  # the captured reset copies into these: they must be tensors the env owns
+            setattr(env, name, getattr(env, name).clone())
+        snap = (env._state.clone(), env._obs.clone(), env._gen.get_state(), [getattr(env, k).clone() for k in info_t])
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -451,7 +551,8 @@ class GraphedRollout:
         env._state.copy_(snap[0])
         env._obs.copy_(snap[1])
         env._gen.set_state(snap[2])
-        env._list_idx = snap[3]
+        for name, t in zip(info_t, snap[3]):
+            getattr(env, name).copy_(t)
         if env.stats is not None:
             env.stats.totals.zero_()
             env.stats.ep_return.zero_()
