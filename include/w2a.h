@@ -201,6 +201,30 @@ int w2a_reset_host(w2a_ctx* ctx, const int32_t* loc, const int32_t* year,
                    int32_t* remaining);
 int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward,
                   uint8_t* terminated, int32_t* remaining, uint8_t* at_budget);
+/* ---- feature engineering: the feature-store columns from raw daily records --------------
+ * Replaces the pandas statements of the reference's ETL, data-processing/merge_state_actions.py:121-210: per-county
+ * percentile rank of the heat index (:122), hinge and interaction terms (:125-133), 3/7-day rolling means and excess
+ * heat (:136-147), day of summer (:151), alert history -- 14-day count, lag, streak (:154-172) --, weekend flag (:178),
+ * remaining budget (:190-196) and the standardised cubic B-spline basis of the day of summer (:198-210).
+ * Rows are sorted by (county, date) as at :23; all arrays are dev.
+ *   county_start  int64 [n_counties + 1]   row offsets of the counties
+ *   max_rows_per_county                    largest county, in rows (<= 6400: one county is staged in shared memory)
+ *   date_days     int32 [n_rows]           days since 1970-01-01
+ *   himax_c       float64 [n_rows]         daily maximum heat index in Celsius (`HImax_C`)
+ *   alert         uint8 [n_rows]           an alert was in force that day (`issue.notnull()`, :114)
+ *   issued_in_advance float64 [n_rows]     NaN = none (:175 fills 0)
+ *   holiday       uint8 [n_rows]           host-supplied calendar flag (the reference asks the `holidays` package)
+ *   feat          out float64 [n_rows, 27] the 27 numeric feature-store columns in merged-frame order (observation
+ *                                          slots 0..26: `exogenous_states` then `endogenous_states_actions`, :228-272)
+ *   year          out int32 [n_rows]       calendar year of the row (:150)
+ *   workspace     dev, W2A_FEATURE_WORKSPACE_BYTES
+ * Columns without accumulation are bit-identical to the reference's float64 results; rolling means agree to 1e-12. */
+#define W2A_FEATURE_WORKSPACE_BYTES 4096
+int w2a_engineer_features(w2a_ctx* ctx, void* stream, int64_t n_rows, int n_counties, const int64_t* county_start,
+                          int max_rows_per_county, const int32_t* date_days, const double* himax_c,
+                          const uint8_t* alert, const double* issued_in_advance, const uint8_t* holiday,
+                          double* feat, int32_t* year, void* workspace);
+
 /* Number of kernels this context has launched (bench.py's `gpu_launches`). */
 int64_t w2a_launch_count(const w2a_ctx* ctx);
 

@@ -18,6 +18,7 @@ STEP_AUTO, STEP_THREAD, STEP_COOP, STEP_TABLE = 0, 1, 2, 3
 POLICY_LEN = 30  # W2A_POLICY_LEN: one weight per observation slot + bias
 BUDGET_DEFAULT = -(2**31)
 OBS_DIM = 29
+FEATURE_WORKSPACE_BYTES = 4096
 
 #: every symbol `include/w2a.h` declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -40,6 +41,7 @@ SIGNATURES = {
     "w2a_host_envs_destroy": (C.c_int, [_P]),
     "w2a_reset_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "w2a_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "w2a_engineer_features": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "w2a_launch_count": (C.c_int64, [_P]),
 }
 

@@ -15,6 +15,7 @@
 #include <new>
 #include <vector>
 
+#include "w2a_features.cuh"
 #include "w2a_kernels.cuh"
 
 namespace {
@@ -665,6 +666,48 @@ int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const d
   a.stochastic = stochastic != 0;
   a.seed = seed;
   return launch_rollout(ctx, stream, n, steps, a, state, ep_return, stats, true);
+}
+
+int w2a_engineer_features(w2a_ctx* ctx, void* stream, int64_t n_rows, int n_counties, const int64_t* county_start,
+                          int max_rows_per_county, const int32_t* date_days, const double* himax_c, const uint8_t* alert,
+                          const double* issued_in_advance, const uint8_t* holiday, double* feat, int32_t* year,
+                          void* workspace) {
+  if (!ctx) return W2A_E_INVALID;
+  if (n_rows == 0 || n_counties == 0) return W2A_OK;
+  if (n_rows < 0 || n_counties < 0 || !county_start || !date_days || !himax_c || !alert || !issued_in_advance || !holiday ||
+      !feat || !year || !workspace)
+    return fail(ctx, W2A_E_INVALID, "w2a_engineer_features: NULL or negative argument");
+  const size_t smem = static_cast<size_t>(max_rows_per_county) * w2a::kFeatRowBytes;
+  if (max_rows_per_county <= 0 || smem > 200 * 1024)
+    return fail(ctx, W2A_E_INVALID, "w2a_engineer_features: max_rows_per_county=%d not in [1, %d] (one county is staged in shared memory)",
+                max_rows_per_county, 200 * 1024 / w2a::kFeatRowBytes);
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned* hist = static_cast<unsigned*>(workspace);
+  double* stats = reinterpret_cast<double*>(static_cast<char*>(workspace) + 2048);
+  W2A_CUDA(ctx, cudaMemsetAsync(workspace, 0, W2A_FEATURE_WORKSPACE_BYTES, st));
+  w2a::FeatArgs a;
+  a.county_start = reinterpret_cast<const long long*>(county_start);
+  a.date_days = date_days;
+  a.himax_c = himax_c;
+  a.alert = alert;
+  a.issued = issued_in_advance;
+  a.holiday = holiday;
+  a.feat = feat;
+  a.year = year;
+  a.hist = hist;
+  a.S = n_counties;
+  a.max_rows = max_rows_per_county;
+  if (smem > 48 * 1024)
+    W2A_CUDA(ctx, cudaFuncSetAttribute(w2a::feature_county_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+  w2a::feature_county_kernel<<<std::min(n_counties, ctx->sm_count * 4), 256, smem, st>>>(a);
+  w2a::bspline_stats_kernel<<<1, 32, 0, st>>>(hist, stats);
+  const int grid = static_cast<int>(std::min<int64_t>((n_rows + 255) / 256, static_cast<int64_t>(ctx->sm_count) * 8));
+  w2a::bspline_apply_kernel<<<grid, 256, 0, st>>>(feat, stats, static_cast<long long>(n_rows));
+  ctx->launches += 3;
+  W2A_CUDA(ctx, cudaGetLastError());
+  return W2A_OK;
 }
 
 int64_t w2a_launch_count(const w2a_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -684,8 +684,8 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #define W2A_TABLE_MINBLOCKS 8  // x 4 warps = 32 warps/SM at 64 registers
 #endif
 #ifndef W2A_TABLE_PREFETCH
-#define W2A_TABLE_PREFETCH 0  // 1: every env asks L2 for tomorrow's record line; 2: and tomorrow's observation row
-#endif
+#define W2A_TABLE_PREFETCH 0  // 1: every env asks L2 for tomorrow's record line; 2: and tomorrow's observation row;
+#endif                        // 3: every CTA bulk-prefetches its share of tomorrow's slice of z_all (sequential HBM reads)
 #ifndef W2A_Z_POLICY
 #define W2A_Z_POLICY 0  // L2 policy of the record gather: 0 default, 1 evict_last
 #endif
@@ -694,6 +694,10 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #endif               // 4 row gather from row 0, 8 no reward / flag outputs
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// bulk (TMA) prefetch of a contiguous, 16-byte aligned block into L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 template <int ADT>
 __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_table_kernel(const StepArgs p) {
@@ -727,6 +731,23 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     a_n = load_action<ADT>(p.action, ec);
   };
   fetch(wg);
+#if W2A_TABLE_PREFETCH == 3
+  // Tomorrow's slice of z_all, streamed into L2 while today's step runs: the CTAs of a full grid split the
+  // slice between them (the day is taken from the CTA's first env: a hint, nothing depends on it), so that
+  // tomorrow's gathers find their lines in L2 instead of fetching them from HBM at random
+  if (threadIdx.x == 0 && gridDim.x >= 64) {
+    const unsigned t_next = (mv_n.y & 0xffu) + 1u;
+    if (t_next < static_cast<unsigned>(p.tb.T)) {
+      const size_t slice = static_cast<size_t>(p.tb.z_day_lines) * 128;
+      const size_t chunk = ((slice + gridDim.x - 1) / gridDim.x + 127) & ~static_cast<size_t>(127);
+      const size_t off = static_cast<size_t>(blockIdx.x) * chunk;
+      if (off < slice) {
+        const char* src = reinterpret_cast<const char*>(p.tb.z_all) + static_cast<size_t>(t_next) * slice + off;
+        bulk_prefetch_l2(src, static_cast<unsigned>(min(chunk, slice - off)));
+      }
+    }
+  }
+#endif
   for (; wg < n_groups; wg += warps_total) {
     const int base = wg << 5;
     const int e = base + lane;
