@@ -63,3 +63,92 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def _fake_tensordict_file(path, tensors):
+    """torch.save of an object that pickles like tensordict.TensorDict (module/class names, NEWOBJ + state)."""
+    import sys
+    import types
+
+    import torch
+
+    mods = {}
+    for mod, cls in (("tensordict._td", "TensorDict"), ("tensordict.utils", "_StringOnlyDict")):
+        m = types.ModuleType(mod)
+        c = type(cls, (dict,), {"__module__": mod})
+        setattr(m, cls, c)
+        mods[mod] = m
+    pkg = types.ModuleType("tensordict")
+    saved = {k: sys.modules.get(k) for k in ("tensordict", *mods)}
+    sys.modules.update({"tensordict": pkg, **mods})
+    try:
+        inner = mods["tensordict.utils"]._StringOnlyDict()
+        inner.update({k: torch.from_numpy(v) for k, v in tensors.items()})
+        td = mods["tensordict._td"].TensorDict()
+        td.__dict__.update({"_device": None, "_tensordict": inner, "_batch_size": torch.Size([3]), "_td_dim_names": None})
+        torch.save(td, path)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_legacy_pt_checkpoint_is_read_without_unpickling_code(tmp_path):
+    """SURVEY 8(f) N2 / VERDICT r1 missing 6: the legacy `posterior_samples.pt` (pickled TensorDict) is read through an
+    allow-list unpickler; the reference's constructor cannot use such a checkpoint (no `baseline_*` keys, no fips_list):
+    `load_weights` fails with the reference's KeyError; anything not on the allow-list is refused."""
+    import pickle
+    import zipfile
+
+    from weather2alert_b200.loading import read_legacy_pt
+
+    rng = np.random.default_rng(0)
+    tensors = {"heat_qi_base": rng.normal(size=(3, 1, 5)).astype(np.float32),
+               "alert_lag1": rng.normal(size=(3, 1, 5)).astype(np.float32),
+               "strided": np.asfortranarray(rng.normal(size=(4, 6))).astype(np.float64)}
+    d = tmp_path / "linear_debug_sim"
+    d.mkdir()
+    _fake_tensordict_file(str(d / "posterior_samples.pt"), tensors)
+    got = read_legacy_pt(str(d / "posterior_samples.pt"))
+    assert set(got) == set(tensors)
+    for k, v in tensors.items():
+        np.testing.assert_array_equal(got[k], v)
+    (d / "config.yaml").write_text("name: linear_debug_sim\nnum_samples: 100\n")
+    with pytest.raises(KeyError):  # env.py:75: config["fips_list"]
+        load_weights("linear_debug_sim", str(tmp_path))
+    (d / "config.yaml").write_text("fips_list: ['01001', '01003', '01005', '01007', '01009']\n")
+    with pytest.raises(KeyError, match="baseline_bias"):  # env.py:85
+        load_weights("linear_debug_sim", str(tmp_path))
+    # a pickle that names anything else is refused before anything runs
+    evil = tmp_path / "evil.pt"
+    with zipfile.ZipFile(evil, "w") as zf:
+        zf.writestr("archive/data.pkl", pickle.dumps(print))
+    with pytest.raises(pickle.UnpicklingError, match="allow-list"):
+        read_legacy_pt(str(evil))
+    ref = "/root/reference/weights/linear_debug_sim/posterior_samples.pt"
+    if os.path.exists(ref):  # the one blob the reference checkout ships: 11 unprefixed keys of [100, 1, 805] float32
+        t = read_legacy_pt(ref)
+        assert len(t) == 11 and all(v.shape == (100, 1, 805) and v.dtype == np.float32 for v in t.values())
+        assert "heat_qi_base" in t and abs(float(t["heat_qi_above_75"].max()) - 58.218) < 1e-2
+
+
+def test_nn_full_medicare_config_without_fips_list_raises_keyerror(tmp_path, golden):
+    """`weights/nn_full_medicare/config.yaml` (the name BASELINE configs[2] uses) has no `fips_list`: the reference
+    raises KeyError at env.py:75, and so does the loader.  The usable layout is `nn_full_medicare_all` (720 counties)."""
+    import yaml
+
+    store, w = golden.store(), golden.weights("std")
+    d = tmp_path / "nn_full_medicare"
+    synthetic.write_reference_files(store, w, str(d))
+    (d / "config.yaml").write_text(yaml.safe_dump({"name": "nn_full_medicare", "num_samples": 100,
+                                                   "arch": {"num_hidden_layers": 1, "hidden_dim": 32}}))
+    with pytest.raises(KeyError, match="fips_list"):
+        load_weights("nn_full_medicare", str(tmp_path))
+    ref = "/root/reference/weights/nn_full_medicare/config.yaml"
+    if os.path.exists(ref):
+        assert "fips_list" not in yaml.safe_load(open(ref))
+        assert len(yaml.safe_load(open("/root/reference/weights/nn_full_medicare_all/config.yaml"))["fips_list"]) == 720
+    nn = open(os.path.join(REPO, "weather2alert_b200", "data", "nn_full_medicare_all_fips.txt")).read().split()
+    assert len(nn) == 720 and len(set(nn)) == 720 and all(len(f) == 5 for f in nn)

@@ -68,6 +68,7 @@ struct w2a_ctx {
   HostEnvs* host = nullptr;
   void* table_scratch = nullptr;  // z_all | x32, owned by the context (step variant TABLE, w2a_precompute_logits)
   std::vector<int32_t> col_to_loc_host;  // host copy of the county map (canonical check of the *_host resets)
+  int64_t keep_state_max_envs = 3 << 20;  // W2A_KEEP_STATE_MAX overrides (0 = never)
   bool pdl = true;                // step kernels are launched with programmatic stream serialization (W2A_PDL=0: off)
   const void* occ_key[kMaxKernels] = {};  // occupancy (CTAs per SM) of each kernel launched so far
   int occ_val[kMaxKernels] = {};
@@ -190,6 +191,9 @@ int step_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const void* action, in
   a.remaining = remaining;
   a.at_budget = at_budget;
   a.n = static_cast<int>(n);
+  // 16 B of state per env are read and 8 B rewritten every step: up to 3M envs (48 MB of the 126 MB L2) they are
+  // kept L2-resident between steps (evict_last), beyond that they stream
+  a.keep_state = n <= ctx->keep_state_max_envs ? 1 : 0;
   switch (action_dtype) {
     case W2A_ACT_U8: return launch_step<0>(ctx, st, a, variant);
     case W2A_ACT_I32: return launch_step<1>(ctx, st, a, variant);
@@ -267,6 +271,7 @@ int w2a_create(int device, w2a_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   const char* pdl_env = std::getenv("W2A_PDL");  // tuning switch: W2A_PDL=0 launches the step kernels fully serialised
   ctx->pdl = !(pdl_env && pdl_env[0] == '0');
+  if (const char* ks = std::getenv("W2A_KEEP_STATE_MAX")) ctx->keep_state_max_envs = std::atoll(ks);
   *out = ctx;
   return W2A_OK;
 }

@@ -71,6 +71,7 @@ struct StepArgs {
   int32_t* remaining;
   uint8_t* at_budget;
   int n;
+  int keep_state;  // the two state planes (16 B/env) are small enough to live in L2 from one step to the next
 };
 
 struct ResetArgs {
@@ -314,6 +315,17 @@ __device__ __forceinline__ double2 ldg_keep(const double2* p, unsigned long long
   double2 v;
   asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
   return v;
+}
+
+// per-env state with an L2 evict_last policy: read and rewritten every step, so for env sets whose 16 B/env fit
+// comfortably in L2 it never has to travel to HBM and back between two steps
+__device__ __forceinline__ uint2 ld_keep_u2(const uint2* p, unsigned long long pol) {
+  uint2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_keep_u2(uint2* p, uint2 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
 }
 
 __device__ __forceinline__ RoundLoads issue_round(const double2* x_lane, const float4* w_lane, unsigned row,
@@ -689,6 +701,9 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #ifndef W2A_Z_POLICY
 #define W2A_Z_POLICY 0  // L2 policy of the record gather: 0 default, 1 evict_last
 #endif
+#ifndef W2A_STATE_KEEP
+#define W2A_STATE_KEEP 1  // per-env state loads/stores carry an L2 evict_last policy when StepArgs::keep_state is set
+#endif
 #ifndef W2A_KNOCK
 #define W2A_KNOCK 0  // timing studies only (results become wrong): 1 no observation store, 2 record gather from line 0,
 #endif               // 4 row gather from row 0, 8 no reward / flag outputs
@@ -724,10 +739,21 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
   // the next group's state and action are in flight while this group's gathers are waited for
   uint2 sv_n, mv_n;
   int a_n;
+#if W2A_STATE_KEEP
+  const unsigned long long keep_state = l2_policy_evict_last();
+#endif
   auto fetch = [&](int group) {
     const int ec = min((group << 5) + lane, p.n - 1);
-    sv_n = ld_stream(p.st_static + ec);
-    mv_n = ld_stream(p.st_mut + ec);
+#if W2A_STATE_KEEP
+    if (p.keep_state) {
+      sv_n = ld_keep_u2(p.st_static + ec, keep_state);
+      mv_n = ld_keep_u2(p.st_mut + ec, keep_state);
+    } else
+#endif
+    {
+      sv_n = ld_stream(p.st_static + ec);
+      mv_n = ld_stream(p.st_mut + ec);
+    }
     a_n = load_action<ADT>(p.action, ec);
   };
   fetch(wg);
@@ -797,6 +823,10 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
       }
     };
     load_rows(0);
+#if W2A_STATE_KEEP
+    if (valid && p.keep_state) st_keep_u2(p.st_mut + e, mv, keep_state);
+    else
+#endif
     if (valid) st_stream(p.st_mut + e, mv);
     if (wg + warps_total < n_groups) fetch(wg + warps_total);
 #if W2A_TABLE_PREFETCH >= 1
