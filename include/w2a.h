@@ -112,9 +112,14 @@ int w2a_set_county_map(w2a_ctx* ctx, const int32_t* col_to_loc);
  * gate): for every day of the summer, every (coefficient column, posterior sample) and every year
  * of the column's county, z_b / z_e in float64 (a float64 GEMM per county and day on the FP64 tensor
  * path), plus the float32 observation row of every day-row (the row copy of _get_obs, env.py:187).
- * The context allocates T * S_w * P * ceil(Y/6) * 128 + S*Y*T * 128 bytes (w2a_precompute_bytes; 3.1 GB
- * for 746 counties x 11 years x 153 days x 100 samples) and enqueues two kernels on `stream`; the
- * tables are valid for work enqueued on that stream afterwards (or after a synchronisation).
+ * Two forms are kept: one 32-byte sector per (day, column, sample, year) with the six agent
+ * coefficients and (z_b, z_e) rounded to float32 -- what the step kernel gathers, one L2 request per
+ * env -- and the float64 pairs, which the kernel falls back to wherever the float32 rounding could
+ * reach the reward (|z| >= 32 that the agent terms pull back out of saturation).
+ * The context allocates T*S_w*P*(Y*32 + ceil(Y/6)*128) + S*Y*T*128 bytes (w2a_precompute_bytes;
+ * 7.1 GB for 746 counties x 11 years x 153 days x 100 samples) and enqueues two kernels on `stream`;
+ * the tables are valid for work enqueued on that stream afterwards (or after a synchronisation) and
+ * are read-only from then on, so W2A_STEP_TABLE launches of one context may run on several streams.
  * Enables W2A_STEP_TABLE.  Needs w2a_set_county_map; any later w2a_set_* call drops the tables.
  * Returns W2A_E_NOMEM (nothing allocated) when the device does not have the room. */
 int w2a_precompute_logits(w2a_ctx* ctx, void* stream);

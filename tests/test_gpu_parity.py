@@ -478,3 +478,53 @@ def test_table_variant_needs_the_precomputed_tables(golden):
     _lib.check(lib.w2a_set_coefs(core.ctx, C.c_void_p(core.w.data_ptr()), core.P, core.Sw), core.ctx)
     with pytest.raises(_lib.W2AError):
         core.step(state, z.to(torch.uint8), obs, reward, term, variant=_lib.STEP_TABLE)
+
+
+def test_table_variant_float32_logits_fall_back_to_float64_where_it_matters():
+    """The step kernel gathers (z_b, z_e) as float32 from the one-sector table; where that rounding could reach the
+    reward -- a huge tabulated logit that the agent terms pull back into the sigmoid's sensitive range -- it must
+    take the float64 pair instead.  Coefficients built for exactly that: bias +-1000 against remaining_budget x -+20
+    with budgets around 50, plus moderate and saturated cases; TABLE against the oracle and against THREAD."""
+    from oracle import heat_alert_oracle as orc
+    from weather2alert_b200 import schema, synthetic
+    from weather2alert_b200.core import HeatAlertCore
+    from weather2alert_b200.store import RewardWeights
+
+    S, Y, P, n = 9, 3, 12, 6000
+    rng = np.random.default_rng(77)
+    fips, zones = synthetic.synthetic_counties(S, seed=5)
+    store = synthetic.make_store(fips, [2006, 2007, 2008], seed=6, zones=zones)
+    coef = synthetic.make_weights(fips, P, seed=7).coef.copy()  # [P, S, 2, 28]
+    rb = schema.SLOT_REMAINING_BUDGET
+    for p in range(P):  # sample p: bias = sign * 20 * B, remaining-budget coefficient = -sign * 20  ->  z crosses 0 near rem = B
+        sign, B = (1.0 if p % 2 else -1.0), (48 + p)
+        for h in (0, 1):
+            coef[p, :, h, 27] += sign * 20.0 * B
+            coef[p, :, h, rb] = -sign * 20.0
+    coef[0] *= 0.01  # one moderate sample (|z| < 32 everywhere)
+    weights = RewardWeights(fips_list=list(fips), coef=coef.astype(np.float32))
+    core = HeatAlertCore(store, weights, "cuda:0")
+    loc = rng.integers(0, S, n).astype(np.int32)
+    idx = dict(loc=loc, year=rng.integers(0, Y, n).astype(np.int32), coef_col=loc.copy(),
+               coef_idx=rng.integers(0, P, n).astype(np.int32), budget=rng.integers(45, 64, n).astype(np.int32))
+    outs = {}
+    for vname in ("table", "thread"):
+        state, obs = core.alloc_state(n), torch.zeros((n, 29), device="cuda")
+        core.reset(state, obs, *(_dev(idx[k]) for k in ("loc", "year", "coef_col", "coef_idx")), budget=_dev(idx["budget"]))
+        st, _ = orc.batch_reset(store.feat, store.sig_code, store.n_days, idx["loc"], idx["year"], idx["coef_col"],
+                                idx["coef_idx"], idx["budget"])
+        reward, term = torch.zeros(n, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+        r2 = np.random.default_rng(1)
+        rews, sensitive = [], 0
+        for i in range(30):
+            act = (r2.random(n) < 0.7).astype(np.uint8)
+            core.step(state, _dev(act), obs, reward, term, variant=VARIANTS[vname])
+            o_ref, r_ref, d_ref, _, _ = orc.batch_step(store.feat, store.sig_code, weights.coef, st, act)
+            assert_obs_equal(obs.cpu().numpy(), o_ref, f"{vname} step {i}")
+            got = reward.cpu().numpy()
+            np.testing.assert_allclose(got, r_ref, rtol=REWARD_RTOL, atol=REWARD_ATOL, err_msg=f"{vname} step {i}")
+            sensitive += int(((np.abs(r_ref) > 1e-3) & (np.abs(r_ref) < 6.0) & (idx["coef_idx"] != 0)).sum())
+            rews.append(got)
+        outs[vname] = np.stack(rews)
+        assert sensitive > 1000  # rewards of the +-1000-bias samples away from both saturations: their logits did cross
+    np.testing.assert_allclose(outs["table"], outs["thread"], rtol=2e-6, atol=REWARD_ATOL)

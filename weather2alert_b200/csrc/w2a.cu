@@ -68,7 +68,7 @@ struct w2a_ctx {
   HostEnvs* host = nullptr;
   void* table_scratch = nullptr;  // z_all | x32, owned by the context (step variant TABLE, w2a_precompute_logits)
   std::vector<int32_t> col_to_loc_host;  // host copy of the county map (canonical check of the *_host resets)
-  int64_t keep_state_max_envs = 3 << 20;  // W2A_KEEP_STATE_MAX overrides (0 = never)
+  int64_t keep_state_max_envs = 3 << 19;  // W2A_KEEP_STATE_MAX overrides (0 = never)
   bool pdl = true;                // step kernels are launched with programmatic stream serialization (W2A_PDL=0: off)
   const void* occ_key[kMaxKernels] = {};  // occupancy (CTAs per SM) of each kernel launched so far
   int occ_val[kMaxKernels] = {};
@@ -191,7 +191,7 @@ int step_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const void* action, in
   a.remaining = remaining;
   a.at_budget = at_budget;
   a.n = static_cast<int>(n);
-  // 16 B of state per env are read and 8 B rewritten every step: up to 3M envs (48 MB of the 126 MB L2) they are
+  // 16 B of state per env are read and 8 B rewritten every step: up to 1.5M envs (24 MB of the 126 MB L2) they are
   // kept L2-resident between steps (evict_last), beyond that they stream
   a.keep_state = n <= ctx->keep_state_max_envs ? 1 : 0;
   switch (action_dtype) {
@@ -296,6 +296,7 @@ static void drop_tables(w2a_ctx* ctx) {
     ctx->table_scratch = nullptr;
   }
   ctx->tb.z_all = nullptr;
+  ctx->tb.z32_all = nullptr;
   ctx->tb.x32 = nullptr;
   ctx->tb.z_lines = 0;
   ctx->tb.z_day_lines = 0;
@@ -366,8 +367,9 @@ size_t w2a_precompute_bytes(const w2a_ctx* ctx) {
   const w2a::Tables& tb = ctx->tb;
   const size_t z_lines = static_cast<size_t>((tb.Y + w2a::kZPerLine - 1) / w2a::kZPerLine);
   const size_t z_bytes = static_cast<size_t>(tb.T) * tb.Sw * tb.P * z_lines * 128;
+  const size_t z32_bytes = static_cast<size_t>(tb.T) * tb.Sw * tb.P * tb.Y * 32;
   const size_t o_bytes = static_cast<size_t>(tb.S) * tb.Y * tb.T * 32 * sizeof(float);
-  return z_bytes + o_bytes;
+  return z_bytes + z32_bytes + o_bytes;
 }
 
 int w2a_precompute_logits(w2a_ctx* ctx, void* stream) {
@@ -384,20 +386,27 @@ int w2a_precompute_logits(w2a_ctx* ctx, void* stream) {
     return fail(ctx, W2A_E_INVALID, "w2a_precompute_logits: %lld table lines exceed the 31-bit line index",
                 static_cast<long long>(day_lines * tb.T));
   const size_t z_bytes = static_cast<size_t>(day_lines) * tb.T * 128;
+  const int64_t entries = static_cast<int64_t>(tb.Sw) * tb.P * tb.Y * tb.T;
+  if (entries >= (int64_t{1} << 32))
+    return fail(ctx, W2A_E_INVALID, "w2a_precompute_logits: %lld table entries exceed the 32-bit entry index",
+                static_cast<long long>(entries));
+  const size_t z32_bytes = static_cast<size_t>(entries) * 32;
   const size_t rows = static_cast<size_t>(tb.S) * tb.Y * tb.T;
   const size_t o_bytes = rows * 32 * sizeof(float);
   size_t free_b = 0, total_b = 0;
   W2A_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-  if (z_bytes + o_bytes + (size_t{1} << 30) > free_b)
+  if (z_bytes + z32_bytes + o_bytes + (size_t{1} << 30) > free_b)
     return fail(ctx, W2A_E_NOMEM, "w2a_precompute_logits: the tables need %.2f GB, %.2f GB are free",
-                (z_bytes + o_bytes) * 1e-9, free_b * 1e-9);
-  W2A_CUDA(ctx, cudaMalloc(&ctx->table_scratch, z_bytes + o_bytes));
+                (z_bytes + z32_bytes + o_bytes) * 1e-9, free_b * 1e-9);
+  W2A_CUDA(ctx, cudaMalloc(&ctx->table_scratch, z_bytes + z32_bytes + o_bytes));
   char* base = static_cast<char*>(ctx->table_scratch);
   float4* z_all = reinterpret_cast<float4*>(base);
-  float* x32 = reinterpret_cast<float*>(base + z_bytes);
-  W2A_CUDA(ctx, cudaMemsetAsync(z_all, 0, z_bytes, st));  // columns without a county keep zero lines
+  float4* z32_all = reinterpret_cast<float4*>(base + z_bytes);
+  float* x32 = reinterpret_cast<float*>(base + z_bytes + z32_bytes);
+  W2A_CUDA(ctx, cudaMemsetAsync(z_all, 0, z_bytes + z32_bytes, st));  // columns without a county keep zero entries
   tb.z_lines = z_lines;
   tb.z_day_lines = static_cast<unsigned>(day_lines);
+  tb.n_records = static_cast<unsigned>(tb.Sw) * static_cast<unsigned>(tb.P);
   {
     const int grid = static_cast<int>(std::min<size_t>((rows + 7) / 8, static_cast<size_t>(ctx->sm_count) * 16));
     w2a::obs_rows_kernel<<<grid, 256, 0, st>>>(tb.x, x32, static_cast<unsigned>(rows));
@@ -407,11 +416,12 @@ int w2a_precompute_logits(w2a_ctx* ctx, void* stream) {
     const int tasks = tb.Sw * ((tb.P + 7) / 8);
     const unsigned gx = static_cast<unsigned>((tasks + w2a::kTableTaskWarps - 1) / w2a::kTableTaskWarps);
     // blockIdx.y = day; at most 65 535 days per launch (T <= 255)
-    w2a::logit_all_kernel<<<dim3(gx, static_cast<unsigned>(tb.T)), 32 * w2a::kTableTaskWarps, 0, st>>>(tb, z_all, 0);
+    w2a::logit_all_kernel<<<dim3(gx, static_cast<unsigned>(tb.T)), 32 * w2a::kTableTaskWarps, 0, st>>>(tb, z_all, z32_all, 0);
     ctx->launches++;
   }
   W2A_CUDA(ctx, cudaGetLastError());
   tb.z_all = z_all;
+  tb.z32_all = z32_all;
   tb.x32 = x32;
   return W2A_OK;
 }

@@ -55,6 +55,13 @@ struct Tables {
   const float4* z_all;
   int z_lines;                // ceil(Y / 6)
   unsigned z_day_lines;       // Sw * P * z_lines: lines per day
+  unsigned n_records;         // Sw * P
+  // z32_all[t][col*P + p][year]: ONE 32-byte sector per (day, column, sample, year) = the six agent coefficients
+  // (lag, streak, remaining budget as (b, e) pairs) + (z_b, z_e) rounded to float32 -- everything an env needs
+  // for its logits in one L2 request.  The float32 rounding (<= 1e-6 below |z| = 32) is inside the reward
+  // tolerance; where it could matter (|z| >= 32 that the agent terms pull back into the sigmoid's sensitive
+  // range) the kernel fetches the float64 pair from z_all instead.
+  const float4* z32_all;
   // x32[row][32]: the float32 observation row (slot order 0..28, significance as NaN / label) of
   // day-row `row` of x: the row copy of _get_obs (env.py:187) is one 128-byte line per env
   const float* x32;
@@ -584,7 +591,7 @@ constexpr int kZPerLine = 6;     // (z_b, z_e) entries per 128-byte line, after 
 #endif
 constexpr int kTableTaskWarps = W2A_TABLE_TASK_WARPS;  // warps (= tasks) per CTA of logit_all_kernel
 #ifndef W2A_TABLE_BUILD_MINBLOCKS
-#define W2A_TABLE_BUILD_MINBLOCKS 6  // x 4 warps = 24 warps/SM at 80 registers
+#define W2A_TABLE_BUILD_MINBLOCKS 4  // x 4 warps; a one-off kernel, sized so that nothing spills
 #endif
 
 // D(8x8) += A(8x4) * B(4x8) in float64 on the tensor cores (DMMA).  Fragments: A[lane/4][lane%4],
@@ -602,7 +609,7 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
 // (coefficients, line heads) is requested before the first wait, the day-rows of the first two year
 // tiles right after.
 __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCKS)
-    logit_all_kernel(const Tables tb, float4* z_all, int t0) {
+    logit_all_kernel(const Tables tb, float4* z_all, float4* z32_all, int t0) {
   const int lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int mtiles = (tb.P + 7) >> 3;
@@ -619,7 +626,10 @@ __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCK
   for (int ks = 0; ks < 6; ++ks) wv[ks] = __ldg(wrec + 4 * ks + tig);
   const float2 bias = __ldg(wrec + 31);
   float4 h = __ldg(reinterpret_cast<const float4*>(wrec) + 14 + (tig & 1));  // lag, streak | remaining budget, bias
+  const float4 c_ls = __ldg(reinterpret_cast<const float4*>(wrec) + 14);     // (b, e) of alert_lag1, alert_streak
+  const float2 c_rem = __ldg(wrec + 30);                                     // (b, e) of remaining_budget
   if (s < 0) return;  // a column without a county in the store: its lines stay zero, no env is canonical on it
+  float4* rec32 = z32_all + ((static_cast<size_t>(t) * tb.Sw * tb.P + static_cast<size_t>(col * tb.P + p)) * tb.Y) * 2;
   float4* rec = z_all + (static_cast<size_t>(t) * tb.z_day_lines + static_cast<size_t>(col * tb.P + p) * tb.z_lines) * 8;
   const double* xday = tb.x + (static_cast<size_t>(s) * tb.Y * tb.T + t) * kXStride;
   const size_t ystride = static_cast<size_t>(tb.T) * kXStride;
@@ -651,8 +661,11 @@ __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCK
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int y = y0 + 2 * tig + i;  // this lane's columns of C
-      if (p_ok && y < tb.Y)
+      if (p_ok && y < tb.Y) {
         reinterpret_cast<double2*>(rec + (y / kZPerLine) * 8 + 2)[y % kZPerLine] = make_double2(cb[i], ce[i]);
+        rec32[2 * y] = c_ls;
+        rec32[2 * y + 1] = make_float4(c_rem.x, c_rem.y, static_cast<float>(cb[i]), static_cast<float>(ce[i]));
+      }
     }
   };
   tile(xb0, g0, 0);
@@ -695,9 +708,6 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #ifndef W2A_TABLE_MINBLOCKS
 #define W2A_TABLE_MINBLOCKS 8  // x 4 warps = 32 warps/SM at 64 registers
 #endif
-#ifndef W2A_TABLE_PREFETCH
-#define W2A_TABLE_PREFETCH 0  // 1: every env asks L2 for tomorrow's record line; 2: and tomorrow's observation row;
-#endif                        // 3: every CTA bulk-prefetches its share of tomorrow's slice of z_all (sequential HBM reads)
 #ifndef W2A_Z_POLICY
 #define W2A_Z_POLICY 0  // L2 policy of the record gather: 0 default, 1 evict_last
 #endif
@@ -706,13 +716,8 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #endif
 #ifndef W2A_KNOCK
 #define W2A_KNOCK 0  // timing studies only (results become wrong): 1 no observation store, 2 record gather from line 0,
-#endif               // 4 row gather from row 0, 8 no reward / flag outputs
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// bulk (TMA) prefetch of a contiguous, 16-byte aligned block into L2
-__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
+#endif               // 4 row gather from row 0, 8 no reward / flag outputs, 16 records of day 0 whatever the day (the
+                     // slice stays in L2), 32 one load per record (head only; no separate (z_b, z_e) request)
 
 template <int ADT>
 __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_table_kernel(const StepArgs p) {
@@ -757,23 +762,6 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     a_n = load_action<ADT>(p.action, ec);
   };
   fetch(wg);
-#if W2A_TABLE_PREFETCH == 3
-  // Tomorrow's slice of z_all, streamed into L2 while today's step runs: the CTAs of a full grid split the
-  // slice between them (the day is taken from the CTA's first env: a hint, nothing depends on it), so that
-  // tomorrow's gathers find their lines in L2 instead of fetching them from HBM at random
-  if (threadIdx.x == 0 && gridDim.x >= 64) {
-    const unsigned t_next = (mv_n.y & 0xffu) + 1u;
-    if (t_next < static_cast<unsigned>(p.tb.T)) {
-      const size_t slice = static_cast<size_t>(p.tb.z_day_lines) * 128;
-      const size_t chunk = ((slice + gridDim.x - 1) / gridDim.x + 127) & ~static_cast<size_t>(127);
-      const size_t off = static_cast<size_t>(blockIdx.x) * chunk;
-      if (off < slice) {
-        const char* src = reinterpret_cast<const char*>(p.tb.z_all) + static_cast<size_t>(t_next) * slice + off;
-        bulk_prefetch_l2(src, static_cast<unsigned>(min(chunk, slice - off)));
-      }
-    }
-  }
-#endif
   for (; wg < n_groups; wg += warps_total) {
     const int base = wg << 5;
     const int e = base + lane;
@@ -789,17 +777,17 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     // ---- every gather of the group is issued before anything waits on one ---------------------------
     // (loads are unconditional -- an env off the fast path reads line 0 and ignores it -- so that no
     // select sits between a load and the next one)
-    const unsigned zl = (yr * 10923u) >> 16;  // year / 6 (exact below 2^14)
-    const unsigned line =
-        (fast && !(W2A_KNOCK & 2)) ? t_before * p.tb.z_day_lines + cv * static_cast<unsigned>(p.tb.z_lines) + zl : 0u;
-    const float4* zrec = p.tb.z_all + static_cast<size_t>(line) * 8;
+    // the env's sector of z32_all: agent coefficients + float32 (z_b, z_e) of its own (day, column, sample, year)
+    const unsigned entry = (fast && !(W2A_KNOCK & 2))
+        ? (((W2A_KNOCK & 16) ? 0u : t_before) * p.tb.n_records + cv) * static_cast<unsigned>(p.tb.Y) + yr
+        : 0u;
+    const float4* zrec = p.tb.z32_all + static_cast<size_t>(entry) * 2;
 #if W2A_Z_POLICY == 1
     const float4 o0 = ldg_keep(zrec, keep);
 #else
     const float4 o0 = __ldg(zrec);
 #endif
-    const float2 o1 = __ldg(reinterpret_cast<const float2*>(zrec + 1));
-    const double2 z = __ldg(reinterpret_cast<const double2*>(zrec + 2) + (fast ? yr - zl * kZPerLine : 0u));
+    const float4 o1 = __ldg(zrec + 1);
     float4 rows[W2A_TABLE_ROWS];  // observation rows: 8 lanes copy one float32 row, four neighbouring envs per round
     auto load_rows = [&](int first) {
 #pragma unroll
@@ -829,14 +817,6 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
 #endif
     if (valid) st_stream(p.st_mut + e, mv);
     if (wg + warps_total < n_groups) fetch(wg + warps_total);
-#if W2A_TABLE_PREFETCH >= 1
-    if (fast && !tr.done) {  // tomorrow's line of this env: a day further in z_all
-      prefetch_l2(zrec + static_cast<size_t>(p.tb.z_day_lines) * 8);
-#if W2A_TABLE_PREFETCH >= 2
-      prefetch_l2(p.tb.x32 + static_cast<size_t>(tr.row + 1) * 32);
-#endif
-    }
-#endif
     const bool write_obs = valid && !tr.done;
     const unsigned wmask = __ballot_sync(kFull, write_obs);
     if (bulk_pending) {  // the previous group's bulk store must have finished reading the staging buffer
@@ -845,7 +825,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
       bulk_pending = false;
     }
     // ---- logits -------------------------------------------------------------------------------
-    double zb = z.x, ze = z.y;
+    double zb = static_cast<double>(o1.z), ze = static_cast<double>(o1.w);
     float lag_b = o0.x, lag_e = o0.y, streak_b = o0.z, streak_e = o0.w, rem_b = o1.x, rem_e = o1.y;
     if (!fast) {  // non-canonical env (similar-county column, Q6): straight from the tables
       const double* xr = p.tb.x + static_cast<size_t>(tr.row) * kXStride;
@@ -866,12 +846,28 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     {
       const double f_lag = static_cast<double>(tr.lag), f_streak = static_cast<double>(tr.streak),
                    f_rem = static_cast<double>(tr.rem);
-      zb = fma(f_lag, static_cast<double>(lag_b), zb);
-      ze = fma(f_lag, static_cast<double>(lag_e), ze);
-      zb = fma(f_streak, static_cast<double>(streak_b), zb);
-      ze = fma(f_streak, static_cast<double>(streak_e), ze);
-      zb = fma(f_rem, static_cast<double>(rem_b), zb);
-      ze = fma(f_rem, static_cast<double>(rem_e), ze);
+      double ab = f_lag * static_cast<double>(lag_b), ae = f_lag * static_cast<double>(lag_e);
+      ab = fma(f_streak, static_cast<double>(streak_b), ab);
+      ae = fma(f_streak, static_cast<double>(streak_e), ae);
+      ab = fma(f_rem, static_cast<double>(rem_b), ab);
+      ae = fma(f_rem, static_cast<double>(rem_e), ae);
+      // The tabulated z is a float32: exact to 1e-6 below |z| = 32.  A bigger |z| only matters if the agent terms
+      // pull the logit back into the range where the sigmoid is not saturated (|z + a| < 30; beyond it the reward
+      // changes by less than 1e-13 relative or is below 1e-12 absolute): then -- and for magnitudes where float32
+      // cannot even tell -- take the float64 pair of z_all.  (+-inf is the closed heat_qi gate: exact as it is.)
+      const float mb = fabsf(o1.z), me = fabsf(o1.w);
+      const bool need_b = mb >= 32.f && mb <= 3.0e38f && (fabs(zb + ab) < 30.0 || mb > 1.0e6f);
+      const bool need_e = me >= 32.f && me <= 3.0e38f && (fabs(ze + ae) < 30.0 || me > 1.0e6f);
+      if (fast && (need_b || need_e)) {
+        const unsigned zl = (yr * 10923u) >> 16;  // year / 6 (exact below 2^14)
+        const float4* line = p.tb.z_all + (static_cast<size_t>(t_before) * p.tb.z_day_lines +
+                                            static_cast<size_t>(cv) * p.tb.z_lines + zl) * 8;
+        const double2 z = __ldg(reinterpret_cast<const double2*>(line + 2) + (yr - zl * kZPerLine));
+        zb = z.x;
+        ze = z.y;
+      }
+      zb += ab;
+      ze += ae;
     }
     if (valid && !(W2A_KNOCK & 8)) {
       __stcs(p.reward + e, step_reward(zb, ze, tr.act));
