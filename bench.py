@@ -434,6 +434,32 @@ def run_ours(args):
                                "HeatAlertVectorEnv(sort_episodes=True), its default for device-sampled resets, produces"}
         del es2
 
+    # ---- HeatAlertVectorEnv with its defaults (device-sampled episodes, sort_episodes on), plain .step() calls ----
+    venv_info = None
+    if not args.no_extras:
+        from weather2alert_b200.vector_env import HeatAlertVectorEnv
+
+        venv = HeatAlertVectorEnv(n, core=core, seed=4321 + rank, similar_climate_counties=wl["augment"])
+        venv.reset()
+        for tt in range(5):
+            venv.step(actions[tt])
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        v0.record()
+        for tt in range(T):  # crosses the end of the summer: the autoreset (draw + sort + reset kernel) is inside
+            venv.step(actions[tt])
+        v1.record()
+        torch.cuda.synchronize()
+        vms = all_max(v0.elapsed_time(v1)) / T
+        venv_info = {"value": n * world / (vms * 1e-3), "unit": UNIT, "ms_per_step": vms,
+                     "roofline_frac": BYTES_STREAMING * n / (vms * 1e-3) / 1e9 / load_peaks()[0],
+                     "kernel": kernel_names[venv._variant()], "sort_episodes": venv.sort_episodes,
+                     "note": "HeatAlertVectorEnv(num_envs, core=...) with default arguments: .step(actions) called from "
+                             "Python 153 times (no CUDA graph), the autoreset of all envs included"}
+        del venv
+
     stats, rollout_info, theta = {}, None, None
     if not args.no_extras:
         # return statistics of one full summer (untimed), then the only collective of the path:
@@ -727,6 +753,7 @@ def run_ours(args):
         "roofline_canonical_466B": {"achieved": ach_c, "frac": ach_c / peak,
                                     "note": "SURVEY 8(d) canonical 466 B/env-step; includes table gathers served from L2"},
         "sorted": sorted_info,
+        "vector_env_default": venv_info,
         "return_stats": {**stats, "reduced_over": world},
         "rollout": rollout_info,
         "single_env": single,

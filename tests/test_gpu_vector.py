@@ -187,7 +187,8 @@ def test_million_envs_properties(big_core):
     o2, r2, m2, s2 = run(2, 0, n)
     ot, rt, mt, st_ = run(3, 0, n)  # per-step logit table variant (all envs canonical and in lock step)
     assert torch.equal(ot.view(torch.int32), o2.view(torch.int32)) and torch.equal(mt, m2) and torch.equal(st_, s2)
-    assert torch.allclose(rt, r2, rtol=1e-6, atol=1e-9)
+    # the table variant gathers (z_b, z_e) as float32 (each exact to 1e-6 below |z| = 32): sums of rewards within 3e-6
+    assert torch.allclose(rt, r2, rtol=3e-6, atol=1e-9)
     assert torch.equal(o1.view(torch.int32), o2.view(torch.int32)) and torch.equal(m1, m2) and torch.equal(s1, s2)
     assert torch.allclose(r1, r2, rtol=1e-6, atol=1e-9)  # float64 sums of float32 rewards; only summation order differs
     o3, r3, m3, s3 = run(2, 0, n)
@@ -336,7 +337,7 @@ def test_vector_env_auto_variant_picks_table(golden, monkeypatch):
         o1, r1, t1, _, i1 = small.step(act)
         o2, r2, t2, _, i2 = forced.step(act)
         assert torch.equal(o1.view(torch.int32), o2.view(torch.int32)) and torch.equal(t1, t2), f"step {i}"
-        assert torch.allclose(r1, r2, rtol=1e-6, atol=1e-10)
+        assert torch.allclose(r1, r2, rtol=3e-6, atol=1e-10)  # table: float32 tabulated logits, see DESIGN.md
     assert (_lib.STEP_TABLE in {k[1] for k in small._bound}) and (_lib.STEP_COOP in {k[1] for k in forced._bound})
 
 

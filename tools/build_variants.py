@@ -12,9 +12,7 @@ from __graft_entry__ import NVCC_FLAGS  # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "pf1": ["-DW2A_TABLE_PREFETCH=1"],
-    "pf2": ["-DW2A_TABLE_PREFETCH=2"],
-    "pf3": ["-DW2A_TABLE_PREFETCH=3"],
+    "z128": ["-DW2A_Z_LOAD=0"],
     "zkeep": ["-DW2A_Z_POLICY=1"],
     "mb6": ["-DW2A_TABLE_MINBLOCKS=6"],
     "rows4mb6": ["-DW2A_TABLE_ROWS=4", "-DW2A_TABLE_MINBLOCKS=6"],

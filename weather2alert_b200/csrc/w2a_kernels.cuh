@@ -708,6 +708,9 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #ifndef W2A_TABLE_MINBLOCKS
 #define W2A_TABLE_MINBLOCKS 8  // x 4 warps = 32 warps/SM at 64 registers
 #endif
+#ifndef W2A_Z_LOAD
+#define W2A_Z_LOAD 1  // how the env's 32-byte sector is fetched: 1 one 256-bit load (LDG.E.256), 0 two 128-bit loads
+#endif
 #ifndef W2A_Z_POLICY
 #define W2A_Z_POLICY 0  // L2 policy of the record gather: 0 default, 1 evict_last
 #endif
@@ -782,12 +785,16 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
         ? (((W2A_KNOCK & 16) ? 0u : t_before) * p.tb.n_records + cv) * static_cast<unsigned>(p.tb.Y) + yr
         : 0u;
     const float4* zrec = p.tb.z32_all + static_cast<size_t>(entry) * 2;
-#if W2A_Z_POLICY == 1
-    const float4 o0 = ldg_keep(zrec, keep);
+#if W2A_Z_LOAD == 1  // one 256-bit load of the sector
+    float4 o0, o1;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(o0.x), "=f"(o0.y), "=f"(o0.z), "=f"(o0.w), "=f"(o1.x), "=f"(o1.y), "=f"(o1.z), "=f"(o1.w)
+                 : "l"(zrec));
+#elif W2A_Z_POLICY == 1
+    const float4 o0 = ldg_keep(zrec, keep), o1 = __ldg(zrec + 1);
 #else
-    const float4 o0 = __ldg(zrec);
+    const float4 o0 = __ldg(zrec), o1 = __ldg(zrec + 1);
 #endif
-    const float4 o1 = __ldg(zrec + 1);
     float4 rows[W2A_TABLE_ROWS];  // observation rows: 8 lanes copy one float32 row, four neighbouring envs per round
     auto load_rows = [&](int first) {
 #pragma unroll
