@@ -152,3 +152,39 @@ def test_nn_full_medicare_config_without_fips_list_raises_keyerror(tmp_path, gol
         assert len(yaml.safe_load(open("/root/reference/weights/nn_full_medicare_all/config.yaml"))["fips_list"]) == 720
     nn = open(os.path.join(REPO, "weather2alert_b200", "data", "nn_full_medicare_all_fips.txt")).read().split()
     assert len(nn) == 720 and len(set(nn)) == 720 and all(len(f) == 5 for f in nn)
+
+
+def test_bench_step_segments_cover_any_steps_and_warmup():
+    """bench.py replays CUDA graphs of step segments so that ANY --steps/--warmup is honoured exactly: a segment never
+    crosses the end of the summer, the reset follows the segment that ends it, and the pieces add up to k steps."""
+    import types
+
+    import bench
+
+    es = types.SimpleNamespace(T=153)
+    seg = lambda t, k: bench.EnvSet.segments(es, t, k)  # noqa: E731
+    assert seg(0, 153) == ([(153, True)], 0)
+    assert seg(0, 20) == ([(20, False)], 20)
+    assert seg(145, 20) == ([(8, True), (12, False)], 12)
+    assert seg(5, 3060) == ([(148, True)] + [(153, True)] * 19 + [(5, False)], 5)
+    t = 5  # the driver's flags: --warmup 5 --steps 20, repeated regions
+    seen = set()
+    for _ in range(70):
+        pieces, t2 = seg(t, 20)
+        assert sum(p[0] for p in pieces) == 20 and all(0 < p[0] <= 153 for p in pieces)
+        assert t2 == (t + 20) % 153 and sum(p[1] for p in pieces) == (1 if t + 20 >= 153 else 0)
+        seen.update(pieces)
+        t = t2
+    assert len(seen) < 30  # a handful of distinct graphs, captured once each
+
+
+def test_bench_nn_layout_tables():
+    """--weights-layout nn: the reference's 720-county list against a 746-county store (BASELINE configs[2])."""
+    import bench
+
+    store, weights = bench.make_tables(years=1, layout="nn", samples=2)
+    assert len(weights.fips_list) == 720 and store.shape[0] == 746
+    assert all(f in store.fips_index for f in weights.fips_list)
+    s = bench.index_streams(store, weights, 1000, 0, False)
+    assert (s["coef_col"] == np.arange(1000) % 720).all()
+    assert (np.array([store.fips[i] for i in s["loc"]]) == np.array(weights.fips_list)[s["coef_col"]]).all()

@@ -21,6 +21,7 @@ VARIANTS = {
     "w2": ["-DW2A_TABLE_WARPS=2", "-DW2A_TABLE_MINBLOCKS=16"],
     "k1": ["-DW2A_KNOCK=1"], "k2": ["-DW2A_KNOCK=2"], "k4": ["-DW2A_KNOCK=4"], "k8": ["-DW2A_KNOCK=8"],
     "k16": ["-DW2A_KNOCK=16"], "k32": ["-DW2A_KNOCK=32"], "k48": ["-DW2A_KNOCK=48"],
+    "k64": ["-DW2A_KNOCK=64"], "k128": ["-DW2A_KNOCK=128"], "rows4": ["-DW2A_TABLE_ROWS=4"],
     "k6": ["-DW2A_KNOCK=6"], "k9": ["-DW2A_KNOCK=9"], "k15": ["-DW2A_KNOCK=15"],
 }
 

@@ -13,7 +13,7 @@ for w in cfg2_4096 cfg4_2m cfg5_8m; do
   python bench.py $Q --workload $w > $O/bench_$w.json 2>> $O/var.err
 done
 python bench.py $Q --workload cfg5_8m --locality sorted > $O/bench_cfg5_8m_sorted.json 2>> $O/var.err
-for v in base k1 k2 k4 k6 k8 k9 k15 k16 z128; do
+for v in base k1 k2 k4 k6 k8 k9 k15 k16 k64 k128 rows4 z128; do
   W2A_LIB_PATH=build/variants/libw2a_$v.so python bench.py $Q > $O/var_$v.json 2>> $O/var.err
 done
 W2A_PDL=0 python bench.py $Q > $O/var_nopdl.json 2>> $O/var.err

@@ -693,6 +693,9 @@ __global__ void __launch_bounds__(256) obs_rows_kernel(const double* __restrict_
   }
 }
 
+#ifndef W2A_Z_LOAD
+#define W2A_Z_LOAD 1  // how the env's 32-byte sector is fetched: 1 one 256-bit load per env (LDG.E.256), 0 two 128-bit loads
+#endif
 struct __align__(128) TableScratchWarp {
   float obs[32 * kObsDim];
 };
@@ -708,9 +711,6 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #ifndef W2A_TABLE_MINBLOCKS
 #define W2A_TABLE_MINBLOCKS 8  // x 4 warps = 32 warps/SM at 64 registers
 #endif
-#ifndef W2A_Z_LOAD
-#define W2A_Z_LOAD 1  // how the env's 32-byte sector is fetched: 1 one 256-bit load (LDG.E.256), 0 two 128-bit loads
-#endif
 #ifndef W2A_Z_POLICY
 #define W2A_Z_POLICY 0  // L2 policy of the record gather: 0 default, 1 evict_last
 #endif
@@ -720,7 +720,7 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #ifndef W2A_KNOCK
 #define W2A_KNOCK 0  // timing studies only (results become wrong): 1 no observation store, 2 record gather from line 0,
 #endif               // 4 row gather from row 0, 8 no reward / flag outputs, 16 records of day 0 whatever the day (the
-                     // slice stays in L2), 32 one load per record (head only; no separate (z_b, z_e) request)
+                     // slice stays in L2), 64 / 128 the record gather with 4 / 1 distinct lines per warp instruction, 32 one load per record (head only; no separate (z_b, z_e) request)
 
 template <int ADT>
 __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_table_kernel(const StepArgs p) {
@@ -784,7 +784,13 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     const unsigned entry = (fast && !(W2A_KNOCK & 2))
         ? (((W2A_KNOCK & 16) ? 0u : t_before) * p.tb.n_records + cv) * static_cast<unsigned>(p.tb.Y) + yr
         : 0u;
+#if W2A_KNOCK & 64   // timing study: the 8 lanes of a group read the group leader's sector (4 distinct lines per load)
+    const float4* zrec = p.tb.z32_all + static_cast<size_t>(__shfl_sync(kFull, entry, lane & 24)) * 2;
+#elif W2A_KNOCK & 128  // timing study: the whole warp reads lane 0's sector (1 line per load)
+    const float4* zrec = p.tb.z32_all + static_cast<size_t>(__shfl_sync(kFull, entry, 0)) * 2;
+#else
     const float4* zrec = p.tb.z32_all + static_cast<size_t>(entry) * 2;
+#endif
 #if W2A_Z_LOAD == 1  // one 256-bit load of the sector
     float4 o0, o1;
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
