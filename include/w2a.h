@@ -114,10 +114,11 @@ int w2a_set_county_map(w2a_ctx* ctx, const int32_t* col_to_loc);
  * path), plus the float32 observation row of every day-row (the row copy of _get_obs, env.py:187).
  * Two forms are kept: one 32-byte sector per (day, column, sample, year) with the six agent
  * coefficients and (z_b, z_e) rounded to float32 -- what the step kernel gathers, one L2 request per
- * env -- and the float64 pairs, which the kernel falls back to wherever the float32 rounding could
- * reach the reward (|z| >= 32 that the agent terms pull back out of saturation).
- * The context allocates T*S_w*P*(Y*32 + ceil(Y/6)*128) + S*Y*T*128 bytes (w2a_precompute_bytes;
- * 7.1 GB for 746 counties x 11 years x 153 days x 100 samples) and enqueues two kernels on `stream`;
+ * env -- and the float64 pairs in episode-major order, which the step kernel falls back to wherever
+ * the float32 rounding could reach the reward (|z| >= 32 that the agent terms pull back out of
+ * saturation) and which w2a_rollout / w2a_rollout_policy stream instead of the day-rows.
+ * The context allocates T*S_w*P*Y*(32 + 16) + S*Y*T*136 bytes (w2a_precompute_bytes;
+ * 6.2 GB for 746 counties x 11 years x 153 days x 100 samples) and enqueues two kernels on `stream`;
  * the tables are valid for work enqueued on that stream afterwards (or after a synchronisation) and
  * are read-only from then on, so W2A_STEP_TABLE launches of one context may run on several streams.
  * Enables W2A_STEP_TABLE.  Needs w2a_set_county_map; any later w2a_set_* call drops the tables.
@@ -173,7 +174,10 @@ int w2a_step(w2a_ctx* ctx, void* stream, int64_t n, const void* action, int acti
  *              of summer of every issued alert, 8-10 count / sum / sum of squares of the lengths
  *              of streaks of issued alerts that ended, 11-13 sums of the day by which 50 %, 80 %,
  *              100 % of a summer's alerts had been issued, 14 summers counted in 11-13 (those
- *              with at least one alert that ran from day 0 within this call) */
+ *              with at least one alert that ran from day 0 within this call)
+ * With the tables of w2a_precompute_logits installed the call is two launches: envs on their own county's column
+ * stream 16 bytes of tabulated float64 logits per env-step (an episode's days are one contiguous run), the others
+ * (similar-county columns, quirk Q6) go through the day-rows as before; every env belongs to exactly one launch. */
 int w2a_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, const uint8_t* actions,
                 uint64_t seed, float p_alert, void* state, double* ep_return, double* stats);
 
@@ -184,7 +188,9 @@ int w2a_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, const uint8_t*
  * the counter-based stream of w2a_rollout).  The observation is the one the reference agent holds before
  * acting: the first observation of the reset, then what each step returned (row of the day just stepped,
  * agent slots after the action; env.py:186-195, quirk Q1), in float64.  Only envs at the start of a summer
- * (fresh from w2a_reset) take part; others are left untouched.
+ * (fresh from w2a_reset) take part; others are left untouched.  With the tables installed the policy's logit over
+ * the 24 table slots is tabulated per day-row first (one pass over the feature store into a context-owned buffer:
+ * one w2a_rollout_policy at a time per context).
  *   policy   dev float64 [W2A_POLICY_LEN] */
 #define W2A_POLICY_LEN 30
 int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const double* policy, int stochastic,

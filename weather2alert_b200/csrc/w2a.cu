@@ -66,7 +66,7 @@ struct w2a_ctx {
   bool have_coefs = false;
   int64_t launches = 0;
   HostEnvs* host = nullptr;
-  void* table_scratch = nullptr;  // z_all | x32, owned by the context (step variant TABLE, w2a_precompute_logits)
+  void* table_scratch = nullptr;  // z32_all | zt_all | x32 | pt, owned by the context (w2a_precompute_logits)
   std::vector<int32_t> col_to_loc_host;  // host copy of the county map (canonical check of the *_host resets)
   int64_t keep_state_max_envs = 3 << 19;  // W2A_KEEP_STATE_MAX overrides (0 = never)
   bool pdl = true;                // step kernels are launched with programmatic stream serialization (W2A_PDL=0: off)
@@ -178,7 +178,7 @@ int step_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const void* action, in
   if (variant == W2A_STEP_AUTO) variant = W2A_STEP_COOP;  // faster than THREAD at every batch size, n = 1 included
   if (variant != W2A_STEP_THREAD && variant != W2A_STEP_COOP && variant != W2A_STEP_TABLE)
     return fail(ctx, W2A_E_INVALID, "w2a_step: unknown variant %d", variant);
-  if (variant == W2A_STEP_TABLE && !ctx->tb.z_all)
+  if (variant == W2A_STEP_TABLE && !ctx->tb.z32_all)
     return fail(ctx, W2A_E_NOTREADY, "w2a_step: W2A_STEP_TABLE needs w2a_set_county_map + w2a_precompute_logits first");
   w2a::StepArgs a;
   a.tb = ctx->tb;
@@ -295,11 +295,11 @@ static void drop_tables(w2a_ctx* ctx) {
     cudaFree(ctx->table_scratch);
     ctx->table_scratch = nullptr;
   }
-  ctx->tb.z_all = nullptr;
   ctx->tb.z32_all = nullptr;
+  ctx->tb.zt_all = nullptr;
   ctx->tb.x32 = nullptr;
-  ctx->tb.z_lines = 0;
-  ctx->tb.z_day_lines = 0;
+  ctx->tb.pt = nullptr;
+  ctx->tb.n_records = 0;
 }
 
 int w2a_set_features(w2a_ctx* ctx, const double* x, const uint8_t* n_days, const int32_t* budget0, int S, int Y,
@@ -362,14 +362,21 @@ int w2a_set_county_map(w2a_ctx* ctx, const int32_t* col_to_loc) {
   return W2A_OK;
 }
 
+namespace {
+struct TableBytes {
+  size_t z32, zt, x32, pt;
+  size_t total() const { return z32 + zt + x32 + pt; }
+};
+TableBytes table_bytes(const w2a::Tables& tb) {
+  const size_t entries = static_cast<size_t>(tb.T) * tb.Sw * tb.P * tb.Y;
+  const size_t rows = static_cast<size_t>(tb.S) * tb.Y * tb.T;
+  return {entries * 32, entries * 16, rows * 32 * sizeof(float), (rows * sizeof(double) + 127) & ~size_t{127}};
+}
+}  // namespace
+
 size_t w2a_precompute_bytes(const w2a_ctx* ctx) {
   if (!ctx || !ctx->have_features || !ctx->have_coefs) return 0;
-  const w2a::Tables& tb = ctx->tb;
-  const size_t z_lines = static_cast<size_t>((tb.Y + w2a::kZPerLine - 1) / w2a::kZPerLine);
-  const size_t z_bytes = static_cast<size_t>(tb.T) * tb.Sw * tb.P * z_lines * 128;
-  const size_t z32_bytes = static_cast<size_t>(tb.T) * tb.Sw * tb.P * tb.Y * 32;
-  const size_t o_bytes = static_cast<size_t>(tb.S) * tb.Y * tb.T * 32 * sizeof(float);
-  return z_bytes + z32_bytes + o_bytes;
+  return table_bytes(ctx->tb).total();
 }
 
 int w2a_precompute_logits(w2a_ctx* ctx, void* stream) {
@@ -380,33 +387,25 @@ int w2a_precompute_logits(w2a_ctx* ctx, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   drop_tables(ctx);
   w2a::Tables& tb = ctx->tb;
-  const int z_lines = (tb.Y + w2a::kZPerLine - 1) / w2a::kZPerLine;
-  const int64_t day_lines = static_cast<int64_t>(tb.Sw) * tb.P * z_lines;
-  if (day_lines * tb.T >= (int64_t{1} << 31))
-    return fail(ctx, W2A_E_INVALID, "w2a_precompute_logits: %lld table lines exceed the 31-bit line index",
-                static_cast<long long>(day_lines * tb.T));
-  const size_t z_bytes = static_cast<size_t>(day_lines) * tb.T * 128;
   const int64_t entries = static_cast<int64_t>(tb.Sw) * tb.P * tb.Y * tb.T;
   if (entries >= (int64_t{1} << 32))
     return fail(ctx, W2A_E_INVALID, "w2a_precompute_logits: %lld table entries exceed the 32-bit entry index",
                 static_cast<long long>(entries));
-  const size_t z32_bytes = static_cast<size_t>(entries) * 32;
-  const size_t rows = static_cast<size_t>(tb.S) * tb.Y * tb.T;
-  const size_t o_bytes = rows * 32 * sizeof(float);
+  const TableBytes b = table_bytes(tb);
   size_t free_b = 0, total_b = 0;
   W2A_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-  if (z_bytes + z32_bytes + o_bytes + (size_t{1} << 30) > free_b)
-    return fail(ctx, W2A_E_NOMEM, "w2a_precompute_logits: the tables need %.2f GB, %.2f GB are free",
-                (z_bytes + z32_bytes + o_bytes) * 1e-9, free_b * 1e-9);
-  W2A_CUDA(ctx, cudaMalloc(&ctx->table_scratch, z_bytes + z32_bytes + o_bytes));
+  if (b.total() + (size_t{1} << 30) > free_b)
+    return fail(ctx, W2A_E_NOMEM, "w2a_precompute_logits: the tables need %.2f GB, %.2f GB are free", b.total() * 1e-9,
+                free_b * 1e-9);
+  W2A_CUDA(ctx, cudaMalloc(&ctx->table_scratch, b.total()));
   char* base = static_cast<char*>(ctx->table_scratch);
-  float4* z_all = reinterpret_cast<float4*>(base);
-  float4* z32_all = reinterpret_cast<float4*>(base + z_bytes);
-  float* x32 = reinterpret_cast<float*>(base + z_bytes + z32_bytes);
-  W2A_CUDA(ctx, cudaMemsetAsync(z_all, 0, z_bytes + z32_bytes, st));  // columns without a county keep zero entries
-  tb.z_lines = z_lines;
-  tb.z_day_lines = static_cast<unsigned>(day_lines);
+  float4* z32_all = reinterpret_cast<float4*>(base);
+  double2* zt_all = reinterpret_cast<double2*>(base + b.z32);
+  float* x32 = reinterpret_cast<float*>(base + b.z32 + b.zt);
+  double* pt = reinterpret_cast<double*>(base + b.z32 + b.zt + b.x32);
+  W2A_CUDA(ctx, cudaMemsetAsync(base, 0, b.z32 + b.zt, st));  // columns without a county keep zero entries
   tb.n_records = static_cast<unsigned>(tb.Sw) * static_cast<unsigned>(tb.P);
+  const size_t rows = static_cast<size_t>(tb.S) * tb.Y * tb.T;
   {
     const int grid = static_cast<int>(std::min<size_t>((rows + 7) / 8, static_cast<size_t>(ctx->sm_count) * 16));
     w2a::obs_rows_kernel<<<grid, 256, 0, st>>>(tb.x, x32, static_cast<unsigned>(rows));
@@ -414,15 +413,21 @@ int w2a_precompute_logits(w2a_ctx* ctx, void* stream) {
   }
   {
     const int tasks = tb.Sw * ((tb.P + 7) / 8);
-    const unsigned gx = static_cast<unsigned>((tasks + w2a::kTableTaskWarps - 1) / w2a::kTableTaskWarps);
-    // blockIdx.y = day; at most 65 535 days per launch (T <= 255)
-    w2a::logit_all_kernel<<<dim3(gx, static_cast<unsigned>(tb.T)), 32 * w2a::kTableTaskWarps, 0, st>>>(tb, z_all, z32_all, 0);
+    const unsigned gy = static_cast<unsigned>((tasks + w2a::kTableTaskWarps - 1) / w2a::kTableTaskWarps);
+    if (gy > 65535u) {
+      cudaFree(ctx->table_scratch);
+      ctx->table_scratch = nullptr;
+      return fail(ctx, W2A_E_INVALID, "w2a_precompute_logits: %d (column, sample block) tasks exceed the launch grid", tasks);
+    }
+    // blockIdx.x = day, blockIdx.y = block of tasks
+    w2a::logit_all_kernel<<<dim3(static_cast<unsigned>(tb.T), gy), 32 * w2a::kTableTaskWarps, 0, st>>>(tb, zt_all, z32_all, 0);
     ctx->launches++;
   }
   W2A_CUDA(ctx, cudaGetLastError());
-  tb.z_all = z_all;
   tb.z32_all = z32_all;
+  tb.zt_all = zt_all;
   tb.x32 = x32;
+  tb.pt = pt;
   return W2A_OK;
 }
 
@@ -587,7 +592,7 @@ int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward
   uint2* smut = plane_mut(h->state, n);
   // one kernel variant for the whole batch, so that chunking never changes a result bit: the tabulated
   // logits when every env steps on its own county's column and the tables exist, else the cooperative kernel
-  const int variant = (ctx->tb.z_all && h->n_noncanon == 0) ? W2A_STEP_TABLE : W2A_STEP_COOP;
+  const int variant = (ctx->tb.z32_all && h->n_noncanon == 0) ? W2A_STEP_TABLE : W2A_STEP_COOP;
   if (h->packed) {
     const size_t un = static_cast<size_t>(n), obs_b = un * W2A_OBS_DIM * sizeof(float);
     cudaStream_t st = h->streams[0];
@@ -642,11 +647,32 @@ int launch_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, w2a::Rollou
   a.n = static_cast<int>(n);
   a.steps = steps;
   int grid = 0;
-  int rc = policy ? grid_for(ctx, w2a::rollout_kernel<true>, 128, 0, 16, n, &grid)
-                  : grid_for(ctx, w2a::rollout_kernel<false>, 128, 0, 16, n, &grid);  // 4 warps x 4 envs per CTA pass
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // with the whole-summer tables the kernels stream 16 B of tabulated logits per env-step (envs on a similar
+  // county's column fall back to the day-rows inside the same launch)
+  const bool tab = ctx->tb.zt_all != nullptr;
+  auto go = [&](auto kernel) {
+    int rc = grid_for(ctx, kernel, 128, 0, 16, n, &grid);  // 4 warps x 4 envs per CTA pass
+    if (rc) return rc;
+    kernel<<<grid, 128, 0, st>>>(a);
+    return W2A_OK;
+  };
+  if (policy && tab) {
+    const unsigned rows = static_cast<unsigned>(ctx->tb.S) * ctx->tb.Y * ctx->tb.T;
+    w2a::policy_rows_kernel<<<std::min<unsigned>((rows + 255) / 256, ctx->sm_count * 8), 256, 0, st>>>(ctx->tb.x, a.policy,
+                                                                                                      ctx->tb.pt, rows);
+    ctx->launches++;
+  }
+  int rc = W2A_OK;
+  if (tab) {  // table launch for the canonical envs, direct launch for the rest (each env belongs to exactly one)
+    a.only = 1;
+    rc = policy ? go(w2a::rollout_kernel<true, true>) : go(w2a::rollout_kernel<false, true>);
+    if (rc) return rc;
+    ctx->launches++;
+    a.only = 2;
+  }
+  rc = policy ? go(w2a::rollout_kernel<true, false>) : go(w2a::rollout_kernel<false, false>);
   if (rc) return rc;
-  if (policy) w2a::rollout_kernel<true><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  else w2a::rollout_kernel<false><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
   ctx->launches++;
   W2A_CUDA(ctx, cudaGetLastError());
   return W2A_OK;

@@ -47,21 +47,22 @@ struct Tables {
   const float* w;
   int S, Y, T, P, Sw;
   const int32_t* col_to_loc;  // [Sw] feature-store county of coefficient column `col`, -1 = none (w2a_set_county_map)
-  // ---- whole-summer tables of step variant TABLE (w2a_precompute_logits), null / 0 before ----------
-  // z_all[t][col*P + p][z_lines] lines of 128 bytes; a line = the 6 agent coefficients (lag, streak,
-  // remaining budget as (b, e) pairs; 24 bytes + 8 zero) followed by the (z_b, z_e) float64 table
-  // parts (gate and bias included) of 6 consecutive years on day t, for the county the column belongs
-  // to: an env finds all it needs for its logits in ONE cache line, whatever day it is on
-  const float4* z_all;
-  int z_lines;                // ceil(Y / 6)
-  unsigned z_day_lines;       // Sw * P * z_lines: lines per day
-  unsigned n_records;         // Sw * P
-  // z32_all[t][col*P + p][year]: ONE 32-byte sector per (day, column, sample, year) = the six agent coefficients
-  // (lag, streak, remaining budget as (b, e) pairs) + (z_b, z_e) rounded to float32 -- everything an env needs
-  // for its logits in one L2 request.  The float32 rounding (<= 1e-6 below |z| = 32) is inside the reward
-  // tolerance; where it could matter (|z| >= 32 that the agent terms pull back into the sigmoid's sensitive
-  // range) the kernel fetches the float64 pair from z_all instead.
+  // ---- whole-summer tables (w2a_precompute_logits), null / 0 before ------------------------------------
+  // For every day t, coefficient record (col*P + p) and year of the column's county: the agent-independent part
+  // of both logits (24 table features, bias and heat_qi gate; env.py:206-217), in two forms:
+  // z32_all[t][col*P + p][year]: ONE 32-byte sector = the six agent coefficients (lag, streak, remaining budget as
+  // (b, e) pairs) + (z_b, z_e) rounded to float32 -- everything an env needs for its logits in one L2 request of
+  // the step kernel.  The float32 rounding (<= 1e-6 below |z| = 32) is inside the reward tolerance; where it could
+  // matter (|z| >= 32 that the agent terms pull back into the sigmoid's sensitive range) the kernel takes the
+  // float64 pair instead.
   const float4* z32_all;
+  // zt_all[(col*P + p)*Y + year][t]: (z_b, z_e) float64, episode-major: the T days of one (record, year) are one
+  // contiguous run -- what the episode-fused rollout streams (16 B per env-step instead of the 256-byte day-row and
+  // a 24-term dot product), and the step kernel's float64 fallback.
+  const double2* zt_all;
+  unsigned n_records;         // Sw * P
+  // pt[row]: the closed-loop policy's table logit of day-row `row` (w2a_rollout_policy computes it per call)
+  double* pt;
   // x32[row][32]: the float32 observation row (slot order 0..28, significance as NaN / label) of
   // day-row `row` of x: the row copy of _get_obs (env.py:187) is one 128-byte line per env
   const float* x32;
@@ -572,9 +573,9 @@ __global__ void __launch_bounds__(32 * kCoopWarps, AHEAD > 4 ? 1 : W2A_COOP_MINB
 // The table part of both logits depends on (county, year, day, posterior sample) only -- never on
 // the agent -- so it is evaluated ONCE for the whole feature store when the tables are installed
 // (w2a_precompute_logits: the reference's per-key loop env.py:206-217 hoisted out of `step`):
-//   logit_all_kernel   z_all[t] line (col*P + p, year / 6) = agent coefficients + (z_b, z_e) of six
-//                      years (gate and bias included), for every day t of the summer -- a float64
-//                      GEMM per (county, day) on the FP64 tensor path (DMMA)
+//   logit_all_kernel   (z_b, z_e) of every (day, column, sample, year), gate and bias included -- a float64
+//                      GEMM per (county, day) on the FP64 tensor path (DMMA) -- written as z32_all (one
+//                      sector per entry, with the agent coefficients) and zt_all (float64, episode-major)
 //   obs_rows_kernel    x32[row][0..28] = the float32 observation row of every day-row
 //   step_table_kernel  per env: transition, z = its entry of ITS OWN day + agent terms, sigmoids,
 //                      reward (one gathered line); per warp: the 32 observation rows are copies of
@@ -585,7 +586,6 @@ __global__ void __launch_bounds__(32 * kCoopWarps, AHEAD > 4 ? 1 : W2A_COOP_MINB
 // directly from x / w (the THREAD kernel's arithmetic): results never depend on the variant.
 // =========================================================================================
 
-constexpr int kZPerLine = 6;     // (z_b, z_e) entries per 128-byte line, after the 32-byte head
 #ifndef W2A_TABLE_TASK_WARPS
 #define W2A_TABLE_TASK_WARPS 4
 #endif
@@ -605,16 +605,18 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
 // The logit table is a small float64 GEMM per (county, day) -- Z[(p, head), y] = W[(p, head), 0..23] .
 // X[y, 0..23]^T, plus the bias and (for z_e) the gate column -- so it runs on the FP64 tensor path:
 // one warp per task = (day, coefficient column, block of 8 posterior samples): 6 k-steps x 2 heads
-// per tile of 8 years of m8n8k4.  blockIdx.y = day.  Everything that depends on the task index alone
+// per tile of 8 years of m8n8k4.  Everything that depends on the task index alone
 // (coefficients, line heads) is requested before the first wait, the day-rows of the first two year
 // tiles right after.
 __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCKS)
-    logit_all_kernel(const Tables tb, float4* z_all, float4* z32_all, int t0) {
+    logit_all_kernel(const Tables tb, double2* zt_all, float4* z32_all, int t0) {
   const int lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int mtiles = (tb.P + 7) >> 3;
-  const int task = blockIdx.x * kTableTaskWarps + (threadIdx.x >> 5);
-  const int t = t0 + static_cast<int>(blockIdx.y);
+  // blockIdx.x = day: the days of one task are scheduled back to back, so their 16-byte zt_all entries (8 days per
+  // line) meet in L2 before the line is written back
+  const int task = blockIdx.y * kTableTaskWarps + (threadIdx.x >> 5);
+  const int t = t0 + static_cast<int>(blockIdx.x);
   if (task >= tb.Sw * mtiles || t >= tb.T) return;
   const int col = task / mtiles, mt = task - col * mtiles;
   const int s = __ldg(tb.col_to_loc + col);
@@ -625,12 +627,11 @@ __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCK
 #pragma unroll
   for (int ks = 0; ks < 6; ++ks) wv[ks] = __ldg(wrec + 4 * ks + tig);
   const float2 bias = __ldg(wrec + 31);
-  float4 h = __ldg(reinterpret_cast<const float4*>(wrec) + 14 + (tig & 1));  // lag, streak | remaining budget, bias
   const float4 c_ls = __ldg(reinterpret_cast<const float4*>(wrec) + 14);     // (b, e) of alert_lag1, alert_streak
   const float2 c_rem = __ldg(wrec + 30);                                     // (b, e) of remaining_budget
   if (s < 0) return;  // a column without a county in the store: its lines stay zero, no env is canonical on it
   float4* rec32 = z32_all + ((static_cast<size_t>(t) * tb.Sw * tb.P + static_cast<size_t>(col * tb.P + p)) * tb.Y) * 2;
-  float4* rec = z_all + (static_cast<size_t>(t) * tb.z_day_lines + static_cast<size_t>(col * tb.P + p) * tb.z_lines) * 8;
+  double2* rect = zt_all + (static_cast<size_t>(col * tb.P + p) * tb.Y) * tb.T + t;  // + year * T
   const double* xday = tb.x + (static_cast<size_t>(s) * tb.Y * tb.T + t) * kXStride;
   const size_t ystride = static_cast<size_t>(tb.T) * kXStride;
   // year tiles of 8: B fragments x[y0 + gid][4*ks + tig] and, for this lane's two columns of C,
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCK
     for (int i = 0; i < 2; ++i) {
       const int y = y0 + 2 * tig + i;  // this lane's columns of C
       if (p_ok && y < tb.Y) {
-        reinterpret_cast<double2*>(rec + (y / kZPerLine) * 8 + 2)[y % kZPerLine] = make_double2(cb[i], ce[i]);
+        rect[static_cast<size_t>(y) * tb.T] = make_double2(cb[i], ce[i]);
         rec32[2 * y] = c_ls;
         rec32[2 * y + 1] = make_float4(c_rem.x, c_rem.y, static_cast<float>(cb[i]), static_cast<float>(ce[i]));
       }
@@ -673,10 +674,6 @@ __global__ void __launch_bounds__(32 * kTableTaskWarps, W2A_TABLE_BUILD_MINBLOCK
   for (int y0 = 16; y0 < tb.Y; y0 += 8) {
     load_b(xb0, g0, y0);
     tile(xb0, g0, y0);
-  }
-  if (p_ok && tig < 2) {  // line heads: the six agent coefficients, 24 bytes + 8 zero
-    if (tig == 1) h.z = h.w = 0.f;
-    for (int l = 0; l < tb.z_lines; ++l) rec[l * 8 + tig] = h;
   }
 }
 
@@ -867,15 +864,12 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
       // The tabulated z is a float32: exact to 1e-6 below |z| = 32.  A bigger |z| only matters if the agent terms
       // pull the logit back into the range where the sigmoid is not saturated (|z + a| < 30; beyond it the reward
       // changes by less than 1e-13 relative or is below 1e-12 absolute): then -- and for magnitudes where float32
-      // cannot even tell -- take the float64 pair of z_all.  (+-inf is the closed heat_qi gate: exact as it is.)
+      // cannot even tell -- take the float64 pair of zt_all.  (+-inf is the closed heat_qi gate: exact as it is.)
       const float mb = fabsf(o1.z), me = fabsf(o1.w);
       const bool need_b = mb >= 32.f && mb <= 3.0e38f && (fabs(zb + ab) < 30.0 || mb > 1.0e6f);
       const bool need_e = me >= 32.f && me <= 3.0e38f && (fabs(ze + ae) < 30.0 || me > 1.0e6f);
       if (fast && (need_b || need_e)) {
-        const unsigned zl = (yr * 10923u) >> 16;  // year / 6 (exact below 2^14)
-        const float4* line = p.tb.z_all + (static_cast<size_t>(t_before) * p.tb.z_day_lines +
-                                            static_cast<size_t>(cv) * p.tb.z_lines + zl) * 8;
-        const double2 z = __ldg(reinterpret_cast<const double2*>(line + 2) + (yr - zl * kZPerLine));
+        const double2 z = __ldg(p.tb.zt_all + (static_cast<size_t>(cv) * p.tb.Y + yr) * p.tb.T + t_before);
         zb = z.x;
         ze = z.y;
       }
@@ -999,6 +993,26 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
 // Actions come from a [steps, n] byte bank or from a counter-based Bernoulli(p) hash.
 // An env that is already done is left alone (unlike `step`, quirk Q11).
 // =========================================================================================
+// pt[row] = the logistic policy's logit over the 24 table slots of day-row `row` (the agent-independent part of
+// `policy(obs)`): one thread per row, once per w2a_rollout_policy call (the policy changes from call to call)
+__global__ void __launch_bounds__(256) policy_rows_kernel(const double* __restrict__ x, const double* __restrict__ policy,
+                                                          double* __restrict__ pt, unsigned rows) {
+  __shared__ double th[24];
+  if (threadIdx.x < 24) th[threadIdx.x] = policy[slot_of_feature(threadIdx.x)];
+  __syncthreads();
+  for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const double2* xr = reinterpret_cast<const double2*>(x + static_cast<size_t>(r) * kXStride);
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {
+      const double2 v = __ldg(xr + u);
+      acc = fma(v.x, th[2 * u], acc);
+      acc = fma(v.y, th[2 * u + 1], acc);
+    }
+    pt[r] = acc;
+  }
+}
+
 struct RolloutArgs {
   Tables tb;
   const uint2* st_static;
@@ -1013,6 +1027,7 @@ struct RolloutArgs {
   // slot (info["feature_names"] order; slot 27, the significance label, is ignored) and the bias
   const double* policy;
   int stochastic;          // 0: action = logit > 0; 1: action = hash(seed, env, step) < sigmoid(logit) * 2^32
+  int only;                // 0 every env, 1 canonical envs only (the table launch), 2 non-canonical envs only (its direct complement)
 };
 constexpr int kPolicyLen = kObsDim + 1;
 
@@ -1050,8 +1065,12 @@ enum StatIndex {
 // drawn by a logistic policy from the observation the agent holds before acting on day d -- the row of
 // day d-1 (day 0 on days 0 and 1: the observation lags a day, quirk Q1) with the agent slots as the
 // step of day d-1 returned them; only envs at the start of a summer (t = 0) take part.
-template <bool POLICY>
-__global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const RolloutArgs p) {
+// TAB = the table form (the whole-summer tables of w2a_precompute_logits exist): an env on its own county's column
+// (canonical bit) reads (z_b, z_e) of its 8 days as ONE 128-byte run of zt_all -- 16 bytes per env-step instead of a
+// 256-byte day-row and a 24-term dot product -- and the policy's table logit comes from pt[row].  The table kernel
+// leaves non-canonical envs alone (RolloutArgs::only = 1); a second, direct launch (only = 2) takes exactly those.
+template <bool POLICY, bool TAB>
+__global__ void __launch_bounds__(128, TAB ? (POLICY ? 4 : 5) : (POLICY ? 3 : 4)) rollout_kernel(const RolloutArgs p) {
   __shared__ double s_stats[kNumStats];
   __shared__ unsigned char s_days[4][4][32];  // [warp][group][chunk of 8 days]: issued-alert bits of the episode so far (T <= 255)
   if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0.0;
@@ -1082,13 +1101,21 @@ __global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const Roll
     bool done = ((mv.y >> 30) & 1u) != 0 || !valid;
     // the alert-timing quantiles need the whole summer: only for episodes that start in this call
     const bool whole_episode = t == 0;
+    const bool canon = (mv.y >> 31) != 0;  // the env's column is its own county: its logits are tabulated
+    if ((p.only == 1 && !canon) || (p.only == 2 && canon)) done = true;  // the other launch's env
+    const double2* const zt_env =
+        TAB ? p.tb.zt_all + (static_cast<size_t>(sv.y & kRecMask) * p.tb.Y + (sv.y >> 24)) * p.tb.T : nullptr;
 
     // coefficient record -> float64 registers, once per episode
     const float4* wr = reinterpret_cast<const float4*>(p.tb.w + static_cast<size_t>(sv.y & kRecMask) * kWStride);
-    const float4 wa4 = __ldg(wr + q), wb4 = __ldg(wr + 8 + q);
     const float4 o0 = __ldg(wr + 14), o1 = __ldg(wr + 15);  // (b,e) of lag1, streak | remaining, bias
-    const double wab0 = wa4.x, wae0 = wa4.y, wab1 = wa4.z, wae1 = wa4.w;
-    const double wbb0 = wb4.x, wbe0 = wb4.y, wbb1 = wb4.z, wbe1 = wb4.w;
+    // this lane's 8 table coefficients in float64 (direct form only)
+    double wab0 = 0.0, wae0 = 0.0, wab1 = 0.0, wae1 = 0.0, wbb0 = 0.0, wbe0 = 0.0, wbb1 = 0.0, wbe1 = 0.0;
+    if (!TAB) {
+      const float4 wa4 = __ldg(wr + q), wb4 = __ldg(wr + 8 + q);
+      wab0 = wa4.x; wae0 = wa4.y; wab1 = wa4.z; wae1 = wa4.w;
+      wbb0 = wb4.x; wbe0 = wb4.y; wbb1 = wb4.z; wbe1 = wb4.w;
+    }
     const double c_lag_b = o0.x, c_lag_e = o0.y, c_str_b = o0.z, c_str_e = o0.w;
     const double c_rem_b = o1.x, c_rem_e = o1.y, c_bias_b = o1.z, c_bias_e = o1.w;
 
@@ -1120,15 +1147,25 @@ __global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const Roll
       // days this env executes in this chunk: t .. t+nv-1, the last one possibly terminal
       const int nv = live ? min(8, min(p.steps - k, n_days - t)) : 0;
       // ---- table part of the logits of the chunk's days ----------------------------------
-      double pbv[8], pev[8], ptv[POLICY ? 8 : 1];
+      double pbv[TAB ? 1 : 8], pev[TAB ? 1 : 8], ptv[POLICY && !TAB ? 8 : 1];
+      if constexpr (!TAB) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const unsigned row = row0 + static_cast<unsigned>(min(t + j, n_days - 1));
-        const double2* xr = x_lane + static_cast<size_t>(row) * (kXStride / 2);
-        const double2 xa = __ldg(xr), xb = __ldg(xr + 8);
-        pbv[j] = fma(xa.x, wab0, xa.y * wab1) + fma(xb.x, wbb0, xb.y * wbb1);
-        pev[j] = fma(xa.x, wae0, xa.y * wae1) + fma(xb.x, wbe0, xb.y * wbe1);
-        if (POLICY) ptv[j] = fma(xa.x, th_a0, xa.y * th_a1) + fma(xb.x, th_b0, xb.y * th_b1);
+        for (int j = 0; j < 8; ++j) {
+          const unsigned row = row0 + static_cast<unsigned>(min(t + j, n_days - 1));
+          const double2* xr = x_lane + static_cast<size_t>(row) * (kXStride / 2);
+          const double2 xa = __ldg(xr), xb = __ldg(xr + 8);
+          pbv[j] = fma(xa.x, wab0, xa.y * wab1) + fma(xb.x, wbb0, xb.y * wbb1);
+          pev[j] = fma(xa.x, wae0, xa.y * wae1) + fma(xb.x, wbe0, xb.y * wbe1);
+          if (POLICY && !TAB) ptv[j] = fma(xa.x, th_a0, xa.y * th_a1) + fma(xb.x, th_b0, xb.y * th_b1);
+        }
+      }
+      // table form: lane q fetches day q of the chunk -- the env's 8 days are one contiguous 128-byte run
+      double2 z_tab = make_double2(0.0, 0.0);
+      double pt_tab = 0.0;
+      if constexpr (TAB) {
+        const int dq = min(t + q, n_days - 1);
+        z_tab = __ldg(zt_env + dq);
+        if (POLICY) pt_tab = __ldg(p.tb.pt + row0 + dq);
       }
       unsigned actm = 0, refm = 0;
       if (!POLICY) {
@@ -1152,14 +1189,18 @@ __global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const Roll
         }
       } else {
         // ---- the policy's table logits of the chunk's rows, one per lane, then known to every lane ----
-        double t8[8];
+        double t2[2] = {pt_tab, 0.0};
+        if constexpr (!TAB) {
+          double t8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t8[j] = ptv[j];
-        fold_level<8>(t8, (q & 4) != 0, 4);
-        double t4[4] = {t8[0], t8[1], t8[2], t8[3]};
-        fold_level<4>(t4, (q & 2) != 0, 2);
-        double t2[2] = {t4[0], t4[1]};
-        fold_level<2>(t2, (q & 1) != 0, 1);
+          for (int j = 0; j < 8; ++j) t8[j] = ptv[j];
+          fold_level<8>(t8, (q & 4) != 0, 4);
+          double t4[4] = {t8[0], t8[1], t8[2], t8[3]};
+          fold_level<4>(t4, (q & 2) != 0, 2);
+          t2[0] = t4[0];
+          t2[1] = t4[1];
+          fold_level<2>(t2, (q & 1) != 0, 1);
+        }
         double ptall[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) ptall[j] = __shfl_sync(kFull, t2[0], (lane & 24) + j);
@@ -1200,14 +1241,18 @@ __global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const Roll
         pt_prev = ptall[7];
       }
       // ---- transpose: lane q gets the table logits of day q ---------------------------------
-      fold_level<8>(pbv, (q & 4) != 0, 4);
-      fold_level<8>(pev, (q & 4) != 0, 4);
-      double b4[4] = {pbv[0], pbv[1], pbv[2], pbv[3]}, e4[4] = {pev[0], pev[1], pev[2], pev[3]};
-      fold_level<4>(b4, (q & 2) != 0, 2);
-      fold_level<4>(e4, (q & 2) != 0, 2);
-      double b2[2] = {b4[0], b4[1]}, e2[2] = {e4[0], e4[1]};
-      fold_level<2>(b2, (q & 1) != 0, 1);
-      fold_level<2>(e2, (q & 1) != 0, 1);
+      double b2[2] = {0.0, 0.0}, e2[2] = {0.0, 0.0};
+      if constexpr (!TAB) {
+        fold_level<8>(pbv, (q & 4) != 0, 4);
+        fold_level<8>(pev, (q & 4) != 0, 4);
+        double b4[4] = {pbv[0], pbv[1], pbv[2], pbv[3]}, e4[4] = {pev[0], pev[1], pev[2], pev[3]};
+        fold_level<4>(b4, (q & 2) != 0, 2);
+        fold_level<4>(e4, (q & 2) != 0, 2);
+        b2[0] = b4[0]; b2[1] = b4[1];
+        e2[0] = e4[0]; e2[1] = e4[1];
+        fold_level<2>(b2, (q & 1) != 0, 1);
+        fold_level<2>(e2, (q & 1) != 0, 1);
+      }
       // ---- lane q evaluates day q (env.py:190-193, 206-221; quirk Q1) --------------------------
       double r_mine = 0.0;
       if (q < nv) {
@@ -1218,7 +1263,8 @@ __global__ void __launch_bounds__(128, POLICY ? 3 : 4) rollout_kernel(const Roll
         const int streak_q = zeros == 0u ? streak + q : q - 1 - (31 - __clz(zeros));
         const int day = t + q;
         const int lag = day > 0 ? act : 0;
-        double zb = b2[0] + c_bias_b, ze = e2[0] + c_bias_e;
+        // the tabulated pair already holds bias and gate; the folded dot products hold the gate only
+        double zb = TAB ? z_tab.x : b2[0] + c_bias_b, ze = TAB ? z_tab.y : e2[0] + c_bias_e;
         zb = fma(static_cast<double>(lag), c_lag_b, zb);
         ze = fma(static_cast<double>(lag), c_lag_e, ze);
         zb = fma(static_cast<double>(streak_q), c_str_b, zb);
