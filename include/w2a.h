@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define W2A_VERSION 200 /* 0.2.0: + w2a_precompute_logits (whole-summer tables; W2A_STEP_TABLE no longer builds per step) */
+#define W2A_VERSION 200 /* 0.2.0: + w2a_precompute_logits (whole-summer tables; W2A_STEP_TABLE no longer builds per step),
+                           w2a_engineer_features, w2a_policy_mlp */
 
 #define W2A_OK 0
 #define W2A_E_INVALID (-1)  /* bad argument (null pointer, size, dtype, variant) */
@@ -195,6 +196,21 @@ int w2a_rollout(w2a_ctx* ctx, void* stream, int64_t n, int steps, const uint8_t*
 #define W2A_POLICY_LEN 30
 int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const double* policy, int stochastic,
                        uint64_t seed, void* state, double* ep_return, double* stats);
+
+/* A small MLP policy on the observation, for the step-by-step loop `a = policy(obs); env.step(a)` (env.py:273-276 with a
+ * policy in place of `action_space.sample()`): one launch computes
+ *   logit = w2 . act(W1 . nan_to_num(obs) + b1) + b2,   action = logit > 0
+ * (or, stochastic, action = hash(seed, env, step) < sigmoid(logit) * 2^32 -- the counter-based stream of w2a_rollout)
+ * for n envs.  The 29 -> hidden contraction runs on the tensor cores in TF32 with float32 accumulation (inputs and W1
+ * are rounded to a 10-bit mantissa; evaluate the policy the same way when training on these rollouts).
+ *   obs      dev float32 [n, 29]   (what w2a_step / w2a_reset wrote; NaN slots count as 0)
+ *   w1       dev float32 [hidden, 29] row-major, b1 / w2 dev float32 [hidden]; hidden: multiple of 8, at most 64
+ *   action   out dev uint8 [n];  logit  out dev float32 [n] or NULL */
+#define W2A_ACT_RELU 0
+#define W2A_ACT_TANH 1
+int w2a_policy_mlp(w2a_ctx* ctx, void* stream, int64_t n, const float* obs, const float* w1, const float* b1,
+                   const float* w2, float b2, int hidden, int activation, int stochastic, uint64_t seed, uint32_t step,
+                   uint8_t* action, float* logit);
 
 /* ---- host-buffer entry points: the call a CPU-side RL loop makes ------------------
  * The context owns a device-resident env set; every call copies its inputs from and its

@@ -187,6 +187,24 @@ class HeatAlertCore:
                                                 int(seed) & (2**64 - 1), _ptr(state), _ptr(ep_return), _ptr(stats)),
                    self.ctx)
 
+    def policy_mlp(self, obs, w1, b1, w2, b2: float, action, logit=None, activation: str = "relu",
+                   stochastic: bool = False, seed: int = 0, step: int = 0):
+        """`action = [w2 . act(W1 . nan_to_num(obs) + b1) + b2 > 0]` for every env in one launch (`w2a_policy_mlp`; the
+        contraction runs on the tensor cores in TF32).  `w1` float32 [H, 29] (torch.nn.Linear layout), `b1`, `w2`
+        float32 [H], H a multiple of 8 up to 64; `action` uint8 [n] out, `logit` float32 [n] out or None."""
+        n = action.numel()
+        H = b1.numel()
+        self._check_dev("obs", obs, torch.float32, n * _lib.OBS_DIM)
+        self._check_dev("w1", w1, torch.float32, H * _lib.OBS_DIM)
+        self._check_dev("b1", b1, torch.float32, H)
+        self._check_dev("w2", w2, torch.float32, H)
+        self._check_dev("action", action, (torch.uint8, torch.bool), n)
+        self._check_dev("logit", logit, torch.float32, n)
+        act = {"relu": 0, "tanh": 1}[activation]
+        _lib.check(self._lib.w2a_policy_mlp(self.ctx, self._stream(), n, _ptr(obs), _ptr(w1), _ptr(b1), _ptr(w2), float(b2),
+                                            H, act, int(bool(stochastic)), int(seed) & (2**64 - 1), int(step) & 0xFFFFFFFF,
+                                            _ptr(action), _ptr(logit)), self.ctx)
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.w2a_launch_count(self.ctx))

@@ -17,6 +17,7 @@
 
 #include "w2a_features.cuh"
 #include "w2a_kernels.cuh"
+#include "w2a_policy.cuh"
 
 namespace {
 
@@ -747,6 +748,43 @@ int w2a_engineer_features(w2a_ctx* ctx, void* stream, int64_t n_rows, int n_coun
   const int grid = static_cast<int>(std::min<int64_t>((n_rows + 255) / 256, static_cast<int64_t>(ctx->sm_count) * 8));
   w2a::bspline_apply_kernel<<<grid, 256, 0, st>>>(feat, stats, static_cast<long long>(n_rows));
   ctx->launches += 3;
+  W2A_CUDA(ctx, cudaGetLastError());
+  return W2A_OK;
+}
+
+int w2a_policy_mlp(w2a_ctx* ctx, void* stream, int64_t n, const float* obs, const float* w1, const float* b1,
+                   const float* w2, float b2, int hidden, int activation, int stochastic, uint64_t seed, uint32_t step,
+                   uint8_t* action, float* logit) {
+  if (!ctx) return W2A_E_INVALID;
+  if (n == 0) return W2A_OK;
+  if (n < 0 || n >= (int64_t{1} << 31) - 64 || !obs || !w1 || !b1 || !w2 || !action)
+    return fail(ctx, W2A_E_INVALID, "w2a_policy_mlp: NULL argument or n out of range");
+  if (hidden < 8 || hidden > w2a::kPolMaxHidden || (hidden & 7))
+    return fail(ctx, W2A_E_INVALID, "w2a_policy_mlp: hidden=%d must be a multiple of 8 in [8, %d]", hidden, w2a::kPolMaxHidden);
+  if (activation != W2A_ACT_RELU && activation != W2A_ACT_TANH)
+    return fail(ctx, W2A_E_INVALID, "w2a_policy_mlp: unknown activation %d", activation);
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  w2a::PolicyMlpArgs a;
+  a.obs = obs;
+  a.w1 = w1;
+  a.b1 = b1;
+  a.w2 = w2;
+  a.b2 = b2;
+  a.hidden = hidden;
+  a.activation = activation;
+  a.stochastic = stochastic != 0;
+  a.seed = seed;
+  a.step = step;
+  a.action = action;
+  a.logit = logit;
+  a.n = static_cast<int>(n);
+  constexpr int kBlock = 32 * w2a::kPolWarps;
+  const size_t smem = sizeof(w2a::PolicyScratch);
+  int grid = 0;
+  int rc = grid_for(ctx, w2a::policy_mlp_kernel, kBlock, smem, kBlock, n, &grid);
+  if (rc) return rc;
+  W2A_CUDA(ctx, launch_kernel(w2a::policy_mlp_kernel, grid, kBlock, smem, static_cast<cudaStream_t>(stream), ctx->pdl, a));
+  ctx->launches++;
   W2A_CUDA(ctx, cudaGetLastError());
   return W2A_OK;
 }

@@ -418,6 +418,34 @@ class HeatAlertVectorEnv(VectorEnv):
         self._step_no += steps
         return ep_return, stats
 
+    # ---- a fused MLP policy for the step-by-step loop ----------------------------------------------------
+    def mlp_policy(self, w1, b1, w2, b2: float, activation: str = "relu", stochastic: bool = False, seed: int = 0):
+        """`policy(obs) -> actions` as ONE kernel launch (`w2a_policy_mlp`): ``logit = w2 . act(W1 . nan_to_num(obs) + b1)
+        + b2``, ``action = logit > 0`` -- or a Bernoulli(sigmoid(logit)) draw from the counter-based stream of `seed`,
+        whose step counter advances with every call.  `w1` is ``[H, 29]`` (torch.nn.Linear layout), H a multiple of 8 up
+        to 64; the contraction runs on the tensor cores in TF32.  The returned callable has `.logits` (float32 [N], the
+        last call's) and works with `graphed_rollout` (capturable; a captured stochastic policy replays the same draws
+        every summer, so re-capture or use the deterministic form there)."""
+        dev, n = self.device, self.num_envs
+        f32 = lambda a: torch.as_tensor(a, dtype=torch.float32).to(dev).contiguous()  # noqa: E731
+        w1_t, b1_t, w2_t = f32(w1), f32(b1).reshape(-1), f32(w2).reshape(-1)
+        H = b1_t.numel()
+        if w1_t.shape != (H, schema.OBS_DIM) or w2_t.numel() != H:
+            raise ValueError(f"mlp_policy: w1 must be [{H}, {schema.OBS_DIM}], b1 and w2 [{H}]")
+        act = torch.zeros(n, dtype=torch.uint8, device=dev)
+        logits = torch.zeros(n, dtype=torch.float32, device=dev)
+        core = self.core
+
+        def policy(obs):
+            core.policy_mlp(obs, w1_t, b1_t, w2_t, float(b2), act, logit=logits, activation=activation,
+                            stochastic=stochastic, seed=seed, step=policy.calls)
+            policy.calls += 1
+            return act
+
+        policy.calls = 0
+        policy.logits = logits
+        return policy
+
     # ---- policy in the loop, replayed as one CUDA graph ------------------------------------------------
     def graphed_rollout(self, policy, steps: int | None = None, reset_at_end: bool = False):
         """Capture `steps` iterations of ``actions = policy(obs); env.step(actions)`` into ONE CUDA
