@@ -527,7 +527,7 @@ def run_ours(args):
     # ---- policy in the loop (BASELINE configs[4] style): a small torch MLP policy on the observations and
     # the step kernel, a whole summer + reset captured in ONE CUDA graph (HeatAlertVectorEnv.graphed_rollout)
     policy_info = None
-    if not args.no_e2e and not args.no_extras:
+    if not args.no_extras:
         try:
             from weather2alert_b200.vector_env import HeatAlertVectorEnv
 
@@ -558,7 +558,7 @@ def run_ours(args):
                            "policy": "torch MLP 29-64-1 (fp32 matmuls) on the observation tensor, deterministic threshold",
                            "mode": "policy forward + step kernel x 153 + reset in one CUDA graph"}
             del roll
-            # the same network as ONE fused kernel per step (w2a_policy_mlp: TF32 tensor cores, float32 accumulate)
+            # the same network as ONE fused kernel per step (w2a_policy_mlp: tensor cores, float16 inputs, float32 accumulate)
             venv.reset()
             fused = venv.mlp_policy(pw1.T.contiguous(), torch.zeros(64, device=dev), pw2, 0.0)
             roll = venv.graphed_rollout(fused, reset_at_end=True)
@@ -575,7 +575,7 @@ def run_ours(args):
             policy_info["fused_mlp_policy"] = {
                 "value": n * world * roll.steps / (f_t * 1e-3), "unit": UNIT, "ms_per_summer": f_t,
                 "us_per_step": f_t / roll.steps * 1e3,
-                "policy": "the same 29-64-1 ReLU MLP as one w2a_policy_mlp launch per step (mma.sync TF32, fp32 accumulate)",
+                "policy": "the same 29-64-1 ReLU MLP as one w2a_policy_mlp launch per step (mma.sync f16 inputs, fp32 accumulate)",
                 "mode": "policy kernel + step kernel x 153 + reset in one CUDA graph"}
             del roll, venv
         except Exception as exc:  # an extra: never let it take the headline line down

@@ -201,8 +201,8 @@ int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const d
  * policy in place of `action_space.sample()`): one launch computes
  *   logit = w2 . act(W1 . nan_to_num(obs) + b1) + b2,   action = logit > 0
  * (or, stochastic, action = hash(seed, env, step) < sigmoid(logit) * 2^32 -- the counter-based stream of w2a_rollout)
- * for n envs.  The 29 -> hidden contraction runs on the tensor cores in TF32 with float32 accumulation (inputs and W1
- * are rounded to a 10-bit mantissa; evaluate the policy the same way when training on these rollouts).
+ * for n envs.  The 29 -> hidden contraction runs on the tensor cores with float16 inputs and float32 accumulation (obs and W1
+ * are rounded to 11 significant bits; evaluate the policy the same way when training on these rollouts).
  *   obs      dev float32 [n, 29]   (what w2a_step / w2a_reset wrote; NaN slots count as 0)
  *   w1       dev float32 [hidden, 29] row-major, b1 / w2 dev float32 [hidden]; hidden: multiple of 8, at most 64
  *   action   out dev uint8 [n];  logit  out dev float32 [n] or NULL */

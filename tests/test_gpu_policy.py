@@ -1,4 +1,4 @@
-"""The fused MLP policy kernel (`w2a_policy_mlp`, tensor cores in TF32) against a plain PyTorch float32 reference of the
+"""The fused MLP policy kernel (`w2a_policy_mlp`, tensor cores, float16 inputs) against a plain PyTorch float32 reference of the
 same op, and inside the step loop / a CUDA graph."""
 import numpy as np
 import pytest
@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _ref_logits(obs, w1, b1, w2, b2, activation):
-    """float64 reference of logit = w2 . act(W1 . nan_to_num(obs) + b1) + b2, and the magnitude TF32 rounding scales with."""
+    """float64 reference of logit = w2 . act(W1 . nan_to_num(obs) + b1) + b2, and the magnitude the float16 input rounding scales with."""
     x = torch.nan_to_num(obs.double(), nan=0.0)
     pre = x @ w1.double().T + b1.double()
     hid = torch.relu(pre) if activation == "relu" else torch.tanh(pre)
@@ -34,7 +34,7 @@ def test_policy_mlp_matches_a_torch_reference(golden, n, H, activation):
     act = pol(obs).clone()
     ref, mag = _ref_logits(obs, w1, b1, w2, -0.1, activation)
     err = (pol.logits.double() - ref).abs()
-    tol = 2.0 ** -9 * mag + 1e-5  # TF32: both operands rounded to 11 significant bits, float32 accumulation
+    tol = 2.0 ** -9 * mag + 1e-5  # float16 inputs: both operands rounded to 11 significant bits, float32 accumulation
     assert bool((err <= tol).all()), float((err / tol).max())
     assert float(err.max()) < 0.05
     sure = ref.abs() > tol

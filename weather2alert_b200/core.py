@@ -190,7 +190,7 @@ class HeatAlertCore:
     def policy_mlp(self, obs, w1, b1, w2, b2: float, action, logit=None, activation: str = "relu",
                    stochastic: bool = False, seed: int = 0, step: int = 0):
         """`action = [w2 . act(W1 . nan_to_num(obs) + b1) + b2 > 0]` for every env in one launch (`w2a_policy_mlp`; the
-        contraction runs on the tensor cores in TF32).  `w1` float32 [H, 29] (torch.nn.Linear layout), `b1`, `w2`
+        contraction runs on the tensor cores, float16 inputs, float32 accumulation).  `w1` float32 [H, 29] (torch.nn.Linear layout), `b1`, `w2`
         float32 [H], H a multiple of 8 up to 64; `action` uint8 [n] out, `logit` float32 [n] out or None."""
         n = action.numel()
         H = b1.numel()

@@ -7,12 +7,13 @@
 // for a batch in one launch, HBM-bound on the 116 observation bytes it reads per env.
 //
 // The 29 -> H contraction is the one dense GEMM of the path ([n, 32] x [32, H], H <= 64) and runs on the tensor
-// cores: `mma.sync.m16n8k8` TF32 with float32 accumulation, a warp per 32 envs (2 m-tiles x H/8 n-tiles x 4 k-steps).
-// The op reads 116 B and does ~4 kFLOP per env (intensity 35 FLOP/B against a ridge of ~210), so the tensor pipe idles
-// most of the time by construction -- the point of using it is to get the 1 900 multiply-adds per env off the FP32
-// pipe (56 us per 2^20 envs there), not to approach its peak; a tcgen05/TMEM pipeline would buy nothing here.
-// Inputs and weights are rounded to TF32 (10-bit mantissa): logits agree with a float32 evaluation to ~1e-3 of the
-// summed |x.w| magnitudes; an agent that trains on these rollouts should evaluate its policy the same way.
+// cores: `mma.sync.m16n8k16` with float16 inputs and float32 accumulation, a warp per 32 envs (2 m-tiles x H/8 n-tiles
+// x 2 k-steps).  The op reads 116 B and does ~4 kFLOP per env (intensity 35 FLOP/B against a ridge of ~210), so the
+// tensor pipe idles most of the time by construction -- the point of using it is to get the 1 900 multiply-adds per
+// env off the FP32 pipe (56 us per 2^20 envs there), not to approach its peak; a tcgen05/TMEM pipeline would buy
+// nothing here.  Inputs and weights are rounded to float16 (11 significant bits, the precision of TF32; observation
+// slots stay far below its range): logits agree with a float32 evaluation to ~1e-3 of the summed |x.w| magnitudes;
+// an agent that trains on these rollouts should evaluate its policy the same way.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,7 +24,7 @@ namespace w2a {
 
 constexpr int kPolMaxHidden = 64;
 constexpr int kPolK = 32;        // 29 observation slots padded to 4 k-steps of 8
-constexpr int kPolWStride = 36;  // shared-memory row stride of W1 (floats): conflict-free B-fragment reads
+constexpr int kPolWStride = 20;  // shared-memory row stride of W1 in half2 words (16 + 4): conflict-free B-fragment reads
 
 struct PolicyMlpArgs {
   const float* obs;   // [n, 29]
@@ -41,22 +42,23 @@ struct PolicyMlpArgs {
   int n;
 };
 
-__device__ __forceinline__ unsigned to_tf32(float x) {
+__device__ __forceinline__ unsigned pack_half2(float lo, float hi) {
   unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
   return r;
 }
-// D(16x8) += A(16x8) * B(8x8), TF32 inputs, float32 accumulate.  A[gid | gid+8][tig | tig+4], B[tig | tig+4][gid],
-// C[gid | gid+8][2*tig + {0,1}]  (gid = lane / 4, tig = lane % 4)
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+// D(16x8) += A(16x16) * B(16x8), float16 inputs (two per register), float32 accumulate.
+// A: a0 = [gid][2tig, 2tig+1], a1 = [gid+8][...], a2 = [gid][2tig+8, +9], a3 = [gid+8][2tig+8, +9];
+// B: b0 = [2tig, 2tig+1][gid], b1 = [2tig+8, 2tig+9][gid];  C[gid | gid+8][2*tig + {0,1}]  (gid = lane / 4, tig = lane % 4)
+__device__ __forceinline__ void mma_f16(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 constexpr int kPolWarps = 4;
 struct __align__(16) PolicyScratch {
-  unsigned w1[kPolMaxHidden * kPolWStride];  // TF32 bit patterns, [h][k], k >= 29 zero
+  unsigned w1[kPolMaxHidden * kPolWStride];  // half2 words, [h][k / 2], k >= 29 zero
   float b1[kPolMaxHidden], w2[kPolMaxHidden];
   float rows[kPolWarps][32 * kObsDim + 4];   // per warp: the 32 observation rows of its group, as in global memory
 };
@@ -68,8 +70,10 @@ __global__ void __launch_bounds__(32 * kPolWarps, 4) policy_mlp_kernel(const Pol
   const int gid = lane >> 2, tig = lane & 3;
   const int H = p.hidden, ntiles = H >> 3;
   for (int i = threadIdx.x; i < kPolMaxHidden * kPolWStride; i += blockDim.x) {
-    const int h = i / kPolWStride, k = i - h * kPolWStride;
-    s.w1[i] = (h < H && k < kObsDim) ? to_tf32(__ldg(p.w1 + h * kObsDim + k)) : 0u;
+    const int h = i / kPolWStride, k = 2 * (i - h * kPolWStride);
+    const float lo = (h < H && k < kObsDim) ? __ldg(p.w1 + h * kObsDim + k) : 0.f;
+    const float hi = (h < H && k + 1 < kObsDim) ? __ldg(p.w1 + h * kObsDim + k + 1) : 0.f;
+    s.w1[i] = pack_half2(lo, hi);
   }
   for (int i = threadIdx.x; i < kPolMaxHidden; i += blockDim.x) {
     s.b1[i] = i < H ? __ldg(p.b1 + i) : 0.f;
@@ -102,24 +106,26 @@ __global__ void __launch_bounds__(32 * kPolWarps, 4) policy_mlp_kernel(const Pol
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[m][j][c] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < kPolK / 8; ++ks) {
+    for (int ks = 0; ks < kPolK / 16; ++ks) {
       unsigned a[2][4];
 #pragma unroll
       for (int m = 0; m < 2; ++m)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int r = 16 * m + gid + 8 * (c & 1), k = 8 * ks + tig + 4 * (c >> 1);
-          float v = k < kObsDim ? rows[r * kObsDim + k] : 0.f;
-          v = v == v ? v : 0.f;  // nan_to_num: the significance slot is NaN when there is no alert
-          a[m][c] = to_tf32(v);
+          const int r = 16 * m + gid + 8 * (c & 1), k = 16 * ks + 2 * tig + 8 * (c >> 1);
+          float v0 = k < kObsDim ? rows[r * kObsDim + k] : 0.f;
+          float v1 = k + 1 < kObsDim ? rows[r * kObsDim + k + 1] : 0.f;
+          v0 = v0 == v0 ? v0 : 0.f;  // nan_to_num: the significance slot is NaN when there is no alert
+          v1 = v1 == v1 ? v1 : 0.f;
+          a[m][c] = pack_half2(v0, v1);
         }
 #pragma unroll
       for (int j = 0; j < kPolMaxHidden / 8; ++j) {
         if (j < ntiles) {
           const unsigned* wrow = s.w1 + (8 * j + gid) * kPolWStride + 8 * ks + tig;
           const unsigned b0 = wrow[0], b1 = wrow[4];
-          mma_tf32(acc[0][j], a[0], b0, b1);
-          mma_tf32(acc[1][j], a[1], b0, b1);
+          mma_f16(acc[0][j], a[0], b0, b1);
+          mma_f16(acc[1][j], a[1], b0, b1);
         }
       }
     }

@@ -423,7 +423,7 @@ class HeatAlertVectorEnv(VectorEnv):
         """`policy(obs) -> actions` as ONE kernel launch (`w2a_policy_mlp`): ``logit = w2 . act(W1 . nan_to_num(obs) + b1)
         + b2``, ``action = logit > 0`` -- or a Bernoulli(sigmoid(logit)) draw from the counter-based stream of `seed`,
         whose step counter advances with every call.  `w1` is ``[H, 29]`` (torch.nn.Linear layout), H a multiple of 8 up
-        to 64; the contraction runs on the tensor cores in TF32.  The returned callable has `.logits` (float32 [N], the
+        to 64; the contraction runs on the tensor cores (float16 inputs, float32 accumulation).  The returned callable has `.logits` (float32 [N], the
         last call's) and works with `graphed_rollout` (capturable; a captured stochastic policy replays the same draws
         every summer, so re-capture or use the deterministic form there)."""
         dev, n = self.device, self.num_envs
@@ -549,10 +549,14 @@ class GraphedRollout:
             self.returns.zero_()
             for _ in range(steps):
                 a = policy(env._obs)
-                self._act.copy_(a.reshape(n).ne(0) if a.dtype != torch.bool else a.reshape(n))
-                step(self._act)
+                if a.dtype == torch.uint8 and a.shape == (n,) and a.is_contiguous():
+                    act = a  # already what the step kernel reads (e.g. `mlp_policy`): no conversion kernels
+                else:
+                    self._act.copy_(a.reshape(n).ne(0) if a.dtype != torch.bool else a.reshape(n))
+                    act = self._act
+                step(act)
                 if env.stats is not None:
-                    env.stats.update(self._act, env._reward, env._term, env._atb)
+                    env.stats.update(act, env._reward, env._term, env._atb)
                 self.returns.add_(env._reward)
             if reset_at_end:
                 s = env._draw()
