@@ -60,7 +60,7 @@ constexpr int kPolWarps = 4;
 struct __align__(16) PolicyScratch {
   unsigned w1[kPolMaxHidden * kPolWStride];  // half2 words, [h][k / 2], k >= 29 zero
   float b1[kPolMaxHidden], w2[kPolMaxHidden];
-  float rows[kPolWarps][32 * kObsDim + 4];   // per warp: the 32 observation rows of its group, as in global memory
+  float rows[kPolWarps][2][32 * kObsDim + 4];  // per warp, double buffered: the 32 observation rows of a group, as in global memory
 };
 
 __global__ void __launch_bounds__(32 * kPolWarps, 4) policy_mlp_kernel(const PolicyMlpArgs p) {
@@ -82,21 +82,38 @@ __global__ void __launch_bounds__(32 * kPolWarps, 4) policy_mlp_kernel(const Pol
   pdl_launch_dependents();
   pdl_wait();  // the observations come from the step launch before this one
   __syncthreads();
-  float* const rows = s.rows[warp];
   const int n_groups = (p.n + 31) >> 5;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  for (int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wg < n_groups; wg += warps_total) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
+  // the rows of group `wg` -> buffer `b`: 32 x 116 contiguous bytes copied as they lie, asynchronously (cp.async, 16 B
+  // per lane and round) when the group is full, so that the next group's rows fly while this one is in the tensor cores
+  auto fetch_rows = [&](int wg, int b) {
+    if (wg >= n_groups) return;
     const int base = wg << 5;
     const int n_valid = min(32, p.n - base);
-    // ---- the group's rows: 32 x 116 contiguous bytes, copied as they lie -----------------------------------
     const float* src = p.obs + static_cast<size_t>(base) * kObsDim;
-    if (n_valid == 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    float* dst = s.rows[warp][b];
+    if (n_valid == 32 && aligned) {
       for (int i = lane; i < 32 * kObsDim / 4; i += 32)
-        reinterpret_cast<float4*>(rows)[i] = __ldcs(reinterpret_cast<const float4*>(src) + i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst + 4 * i))),
+                     "l"(src + 4 * i)
+                     : "memory");
     } else {
-      for (int i = lane; i < 32 * kObsDim; i += 32) rows[i] = i < n_valid * kObsDim ? __ldcs(src + i) : 0.f;
+      for (int i = lane; i < 32 * kObsDim; i += 32) dst[i] = i < n_valid * kObsDim ? __ldcs(src + i) : 0.f;
     }
+  };
+  int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int buf = 0;
+  fetch_rows(wg, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (; wg < n_groups; wg += warps_total, buf ^= 1) {
+    const int base = wg << 5;
+    const int n_valid = min(32, p.n - base);
+    fetch_rows(wg + warps_total, buf ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this group's rows have landed; the next group's are in flight
     __syncwarp();
+    const float* const rows = s.rows[warp][buf];
     // ---- hidden pre-activations: [32, 32] x [32, H] on the tensor cores -----------------------------------
     float acc[2][kPolMaxHidden / 8][4];
 #pragma unroll
