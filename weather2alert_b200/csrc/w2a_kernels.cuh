@@ -5,18 +5,23 @@
 // of independent envs; how they compute it is laid out for B200:
 //
 //   * per-env state is two SoA planes of 8 bytes (static: episode row + coefficient
-//     vector; mutable: remaining budget + packed day/streak/14-day window), so a warp
+//     record + year; mutable: remaining budget + packed day/streak/14-day window), so a warp
 //     reads and writes it with fully coalesced 8-byte accesses;
-//   * both tables are arrays of 256-byte, line-aligned records (one day-row of float64
-//     features; one float32 coefficient vector), so the gather of one env is exactly
-//     four 128-byte lines, each fetched by 8 lanes with one 128-bit load apiece;
-//   * the step kernel gives every env 8 lanes for that gather, accumulates the two
-//     28-term dot products in float64, folds the 8 partials through shared memory, and
-//     stages the 29-slot observations of a warp's 32 envs in shared memory so that they
+//   * everything in the reward that does not depend on the agent is tabulated once for the
+//     whole summer (w2a_precompute_logits: a float64 GEMM per county and day on the FP64
+//     tensor path), so the default step kernel (TABLE) gathers one 32-byte sector and one
+//     128-byte float32 observation row per env, and the episode-fused rollout streams 16
+//     bytes per env-step;
+//   * the cooperative step kernel (COOP: env sets on similar counties' coefficients, which
+//     cannot be tabulated) gathers the two 256-byte, line-aligned records of an env -- one
+//     day-row of float64 features, one float32 coefficient vector: exactly four 128-byte
+//     lines, each fetched by 8 lanes with one 128-bit load apiece -- and accumulates the two
+//     28-term dot products in float64, folding the 8 partials through shared memory;
+//   * the 29-slot observations of a warp's 32 envs are staged in shared memory so that they
 //     leave as one contiguous 3712-byte bulk (TMA) store;
-//   * tables are read through the read-only path and stay L2 resident; the per-env
-//     streams (state, action, obs, reward, flags) use streaming (.cs) accesses so they
-//     do not evict the tables.
+//   * tables are read through the read-only path; the per-env streams (action, obs, reward,
+//     flags) use streaming accesses, the 16 bytes of state per env stay L2-resident between
+//     two steps (evict_last) when the env set is small enough.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, AHEAD > 4 ? 1 : W2A_COOP_MINB
 }
 
 // =========================================================================================
-// step, variant TABLE: one 128-byte record + one 128-byte observation row per env.
+// step, variant TABLE: one 32-byte sector + one 128-byte observation row per env.
 //
 // The table part of both logits depends on (county, year, day, posterior sample) only -- never on
 // the agent -- so it is evaluated ONCE for the whole feature store when the tables are installed
@@ -578,8 +583,8 @@ __global__ void __launch_bounds__(32 * kCoopWarps, AHEAD > 4 ? 1 : W2A_COOP_MINB
 //                      sector per entry, with the agent coefficients) and zt_all (float64, episode-major)
 //   obs_rows_kernel    x32[row][0..28] = the float32 observation row of every day-row
 //   step_table_kernel  per env: transition, z = its entry of ITS OWN day + agent terms, sigmoids,
-//                      reward (one gathered line); per warp: the 32 observation rows are copies of
-//                      x32 rows (one more gathered line per env), patched with the agent slots, and
+//                      reward (one gathered sector); per warp: the 32 observation rows are copies of
+//                      x32 rows (one gathered line per env), patched with the agent slots, and
 //                      leave through one bulk (TMA) store.
 // Every env looks its own day up, so envs need not march in lock step.  An env whose coefficient
 // column is not its own county (augmentation, quirk Q6: no `canonical` bit) computes its logits
@@ -709,15 +714,15 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #define W2A_TABLE_MINBLOCKS 8  // x 4 warps = 32 warps/SM at 64 registers
 #endif
 #ifndef W2A_Z_POLICY
-#define W2A_Z_POLICY 0  // L2 policy of the record gather: 0 default, 1 evict_last
+#define W2A_Z_POLICY 0  // L2 policy of the sector gather (two 128-bit loads only): 0 default, 1 evict_last
 #endif
 #ifndef W2A_STATE_KEEP
 #define W2A_STATE_KEEP 1  // per-env state loads/stores carry an L2 evict_last policy when StepArgs::keep_state is set
 #endif
 #ifndef W2A_KNOCK
-#define W2A_KNOCK 0  // timing studies only (results become wrong): 1 no observation store, 2 record gather from line 0,
-#endif               // 4 row gather from row 0, 8 no reward / flag outputs, 16 records of day 0 whatever the day (the
-                     // slice stays in L2), 64 / 128 the record gather with 4 / 1 distinct lines per warp instruction, 32 one load per record (head only; no separate (z_b, z_e) request)
+#define W2A_KNOCK 0  // timing studies only (results become wrong; profiles/r02/knockouts.txt): 1 no observation store,
+#endif               // 2 sector gather from entry 0, 4 row gather from row 0, 8 no reward / flag outputs, 16 sectors of day 0
+                     // whatever the day (the slice stays in L2), 64 / 128 the sector gather with 4 / 1 distinct lines per load
 
 template <int ADT>
 __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_table_kernel(const StepArgs p) {
