@@ -371,3 +371,34 @@ def test_vector_env_intended_augmentation(golden, monkeypatch):
         o_ref, r_ref, d_ref, _, _ = orc.batch_step(store.feat, store.sig_code, weights.coef, st, act)
         np.testing.assert_array_equal(obs.cpu().numpy(), o_ref.astype(np.float32))
         np.testing.assert_allclose(rew.cpu().numpy(), r_ref, rtol=1e-5, atol=1e-10)
+
+
+def test_index_streams_pick_the_table_variant_when_every_env_is_on_its_own_column(golden, monkeypatch):
+    """Caller-supplied index streams: the vector env checks on the host whether every (county, column) pair is the
+    county's own and only then steps on the tabulated logits; results equal the cooperative kernel's either way."""
+    from weather2alert_b200 import HeatAlertVectorEnv, _lib
+    from weather2alert_b200.core import HeatAlertCore
+
+    monkeypatch.setattr(HeatAlertCore, "TABLE_MIN_ENVS", 1)
+    store, weights = golden.store(), golden.weights("std")
+    n = 300
+    rng = np.random.default_rng(4)
+    col = rng.integers(0, len(weights.fips_list), n)
+    loc = np.array([store.fips_index[weights.fips_list[c]] for c in col])
+    streams = dict(loc=loc, year=rng.integers(0, store.shape[1], n), coef_col=col, coef_idx=rng.integers(0, weights.n_samples, n))
+    streams["year"] = np.where(store.n_days[loc, streams["year"]] == 0, 0, streams["year"])
+    a = HeatAlertVectorEnv(n, weights=weights, store=store, autoreset=False)
+    a.reset(options={"index_streams": streams})
+    assert a._variant() == _lib.STEP_TABLE
+    mixed = dict(streams, coef_col=np.roll(col, 1))  # somebody else's column: not tabulated
+    b = HeatAlertVectorEnv(n, weights=weights, store=store, autoreset=False)
+    b.reset(options={"index_streams": mixed})
+    assert b._variant() == _lib.STEP_AUTO
+    c = HeatAlertVectorEnv(n, weights=weights, store=store, autoreset=False, step_variant=_lib.STEP_COOP)
+    c.reset(options={"index_streams": streams})
+    for i in range(30):
+        act = torch.from_numpy(rng.random(n) < 0.4).cuda()
+        oa, ra, ta, _, _ = a.step(act)
+        oc, rc, tc, _, _ = c.step(act)
+        assert torch.equal(oa.view(torch.int32), oc.view(torch.int32)) and torch.equal(ta, tc)
+        assert torch.allclose(ra, rc, rtol=3e-6, atol=1e-10)

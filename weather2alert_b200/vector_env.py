@@ -177,7 +177,6 @@ class HeatAlertVectorEnv(VectorEnv):
         n, dev, o = self.num_envs, self.device, self._reset_opts
         sp = self.sampler
         if "index_streams" in o:
-            self._canonical = False  # caller-chosen (county, column) pairs: not known to be the county's own
             src = o["index_streams"]
             s = {k: torch.as_tensor(np.ascontiguousarray(src[k], dtype=np.int32)).to(dev)
                  for k in ("loc", "year", "coef_col", "coef_idx")}
@@ -194,6 +193,8 @@ class HeatAlertVectorEnv(VectorEnv):
             if (nd == 0).any():
                 bad = int(np.argmax(nd == 0))
                 raise KeyError((self.store.fips[int(src["loc"][bad])], self.store.years[int(src["year"][bad])]))
+            # every env on its own county's column? then the tabulated logits apply (checked on the host streams)
+            self._canonical = bool((sp.list_to_data[np.asarray(src["coef_col"])] == np.asarray(src["loc"])).all())
             return s
         augment = o.get("similar_climate_counties", self.similar_climate_counties)
         self._canonical = (not augment) or augment == "intended"
