@@ -36,3 +36,13 @@ def test_bench_line_has_the_contract_keys():
     assert set(k) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["rollout"]["same_returns_as_stepping"] is True and d["return_stats"]["episodes"] == 65536
     assert d["single_env"]["ms_per_step"] > 0 and d["single_env"]["steps"] == 153
+    # round 2: the oracle gate ran on the bench's own tables before anything was timed, the timed region is made of
+    # graph-replayed K-step regions, the e2e number is read against the link's own ceiling
+    pg = d["parity"]
+    assert pg["ok"] is True and pg["obs_bit_exact"] is True and pg["envs"] >= 1 << 16 and pg["steps"] >= 10
+    assert pg["max_reward_rel"] <= 1e-5
+    assert d["timing"]["repeats"] >= 1 and "graphs" in d["config"]["mode"]
+    assert e["link_gbs"] > 1 and 0 < e["frac_of_link"] < 1.5
+    assert d["sorted"]["value"] > 0 and d["vector_env_default"]["sort_episodes"] is True
+    assert d["policy_in_loop"]["fused_mlp_policy"]["value"] > d["policy_in_loop"]["value"]
+    assert set(d["other_configs"]) == {"cfg4_2m", "cfg5_8m"} and all("error" not in v for v in d["other_configs"].values())
