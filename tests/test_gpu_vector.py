@@ -323,6 +323,7 @@ def test_vector_env_auto_variant_picks_table(golden, monkeypatch):
     n = 257
     small = HeatAlertVectorEnv(n, weights=weights, store=store, seed=5)
     small.reset()
+    monkeypatch.setattr(HeatAlertCore, "TABLE_MIN_ENVS", 1000)
     assert small._variant() == _lib.STEP_AUTO  # below TABLE_MIN_ENVS
     monkeypatch.setattr(HeatAlertCore, "TABLE_MIN_ENVS", 1)
     assert small._variant() == _lib.STEP_TABLE

@@ -126,9 +126,10 @@ class HeatAlertCore:
                                       _ptr(state), _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(remaining),
                                       _ptr(at_budget), variant), self.ctx)
 
-    # Below this many envs COOP's small-batch instance (every gather of a group in flight at once, warps
-    # spread over the SMs) is the faster launch; the tables themselves cost nothing per step any more.
-    TABLE_MIN_ENVS = 2048
+    # Smallest env set stepped on the tabulated logits.  With the tables in place they win at every size (B200, graph
+    # replay, 60-county tables: 1.95 / 2.37 / 2.46 us per step at 32 / 1 024 / 4 096 envs against COOP's 2.54 / 2.78 /
+    # 3.22; level at 4 096 envs on the 746-county tables), so this is a knob for experiments, not a crossover.
+    TABLE_MIN_ENVS = 1
 
     def choose_variant(self, n: int, canonical: bool) -> int:
         """Resolve STEP_AUTO above the C ABI: TABLE (tabulated logits, one record + one row per env) when
