@@ -122,6 +122,39 @@ __device__ __forceinline__ int load_action(const void* a, int e) {
 // scipy.special.expit in float64, as used at env.py:211,218 (the episode-fused rollout sums float64 returns)
 __device__ __forceinline__ double expit(double z) { return 1.0 / (1.0 + exp(-z)); }
 
+// The same function for the episode-fused kernels, where two (policy: up to ten) of them per env-step are the bulk of
+// the arithmetic: exp(-z) = 2^n * e^g with n = rint(-z log2 e), g = (-z log2 e - n) ln 2 in [-0.347, 0.347] and a
+// degree-10 Taylor polynomial (truncation 2e-13 relative), 2^n by exponent arithmetic, 1 / (1 + e) by the hardware
+// reciprocal seed and two Newton steps: ~25 instructions instead of ~60 for exp() + a float64 division.  Relative
+// error <= 4e-13 for every z (returns are checked against the oracle at 1e-9); z = -1e300 (the closed heat_qi gate)
+// gives 2^-1000 (1 - that is exactly 1), z = +1e300 exactly 1, NaN stays NaN.
+__device__ __forceinline__ double expit_fast(double z) {
+  double t = z * -1.4426950408889634;                 // 2^t = exp(-z)
+  t = fmin(fmax(t, -1000.0), 1000.0);                 // 2^+-1000 are finite doubles; the sigmoid is 0 / 1 out there
+  const double magic = 6755399441055744.0;            // 1.5 * 2^52: t + magic holds rint(t) in its low word
+  const double tn = t + magic;
+  const int n = __double2loint(tn);
+  const double g = (t - (tn - magic)) * 0.6931471805599453;
+  double p = 2.755731922398589e-07;                   // 1/10!
+  p = fma(p, g, 2.7557319223985893e-06);              // 1/9!
+  p = fma(p, g, 2.48015873015873e-05);                // 1/8!
+  p = fma(p, g, 1.984126984126984e-04);               // 1/7!
+  p = fma(p, g, 1.388888888888889e-03);               // 1/6!
+  p = fma(p, g, 8.333333333333333e-03);               // 1/5!
+  p = fma(p, g, 4.1666666666666664e-02);              // 1/4!
+  p = fma(p, g, 1.6666666666666666e-01);              // 1/3!
+  p = fma(p, g, 0.5);
+  p = fma(p, g, 1.0);
+  p = fma(p, g, 1.0);                                 // e^g
+  const double e = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));  // * 2^n (p in [0.7, 1.42])
+  const double d = 1.0 + e;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);                     // Newton: r (2 - d r), twice: 20 -> 40 -> 80 bits
+  r = fma(r, fma(-d, r, 1.0), r);
+  return r;
+}
+
 // The step kernels hand the reward back as float32, so they evaluate the sigmoids in float32 too --
 // but on an argument reduced in float64: t = -z*log2(e) = n + f exactly (|f| <= 1/2), 2^f by
 // MUFU.EX2, 2^n by exponent arithmetic, the reciprocal by MUFU.RCP.  Relative error <= 3e-7 for any
@@ -1222,7 +1255,7 @@ __global__ void __launch_bounds__(128, TAB ? (POLICY ? 4 : 5) : (POLICY ? 3 : 4)
           logit = fma(static_cast<double>(cnt_seen), th_2wks, logit);
           unsigned a;
           if (p.stochastic) {
-            const double thr = expit(logit) * 4294967296.0;
+            const double thr = expit_fast(logit) * 4294967296.0;
             const unsigned thr_u = thr >= 4294967295.0 ? 0xffffffffu : static_cast<unsigned>(thr);
             a = rollout_hash(p.seed, static_cast<unsigned>(e), static_cast<unsigned>(k + j)) < thr_u ? 1u : 0u;
           } else {
@@ -1276,8 +1309,8 @@ __global__ void __launch_bounds__(128, TAB ? (POLICY ? 4 : 5) : (POLICY ? 3 : 4)
         ze = fma(static_cast<double>(streak_q), c_str_e, ze);
         zb = fma(static_cast<double>(rem_after), c_rem_b, zb);
         ze = fma(static_cast<double>(rem_after), c_rem_e, ze);
-        const double baseline = expit(zb);
-        const double eff = act ? expit(ze) : 0.0;
+        const double baseline = expit_fast(zb);
+        const double eff = act ? expit_fast(ze) : 0.0;
         r_mine = kRewardScale * baseline * (1.0 - eff);
         // timing statistics of this day: when alerts are issued, how long streaks of issued alerts last
         if (act) {
