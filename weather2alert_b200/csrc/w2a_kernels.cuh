@@ -1179,11 +1179,31 @@ __global__ void __launch_bounds__(128, TAB ? (POLICY ? 4 : 5) : (POLICY ? 3 : 4)
 
     double ret = 0.0;
     int k = 0;  // steps taken by this env in this call
+    // table form: what lane q needs of a chunk -- (z_b, z_e) of day q, the policy's table logit, the action byte -- is
+    // requested one chunk ahead, so that a chunk never starts by waiting for memory (the env's 8 days are ONE contiguous
+    // 128-byte run of zt_all; the chunk's day range follows from t and k alone)
+    double2 z_nxt = make_double2(0.0, 0.0);
+    double pt_nxt = 0.0;
+    int a_nxt = 0;
+    auto prefetch_chunk = [&](int t0, int k0, bool alive) {
+      if constexpr (TAB) {
+        const int nv0 = alive && k0 < p.steps ? min(8, min(p.steps - k0, n_days - t0)) : 0;
+        const int dq = min(t0 + q, n_days - 1);
+        z_nxt = __ldg(zt_env + dq);
+        if (POLICY) pt_nxt = __ldg(p.tb.pt + row0 + dq);
+        if (!POLICY && p.actions) a_nxt = q < nv0 ? __ldg(p.actions + static_cast<size_t>(k0 + q) * p.n + e) : 0;
+      }
+    };
+    prefetch_chunk(t, 0, !done);
     // the 4 envs of a warp may need different numbers of chunks: loop while any is alive
     while (__any_sync(kFull, !done && k < p.steps)) {
       const bool live = !done && k < p.steps;
       // days this env executes in this chunk: t .. t+nv-1, the last one possibly terminal
       const int nv = live ? min(8, min(p.steps - k, n_days - t)) : 0;
+      const double2 z_tab = z_nxt;
+      const double pt_tab = pt_nxt;
+      const int a_tab = a_nxt;
+      prefetch_chunk(t + nv, k + nv, live && (t + nv) < n_days);  // the next chunk's, in flight during this one
       // ---- table part of the logits of the chunk's days ----------------------------------
       double pbv[TAB ? 1 : 8], pev[TAB ? 1 : 8], ptv[POLICY && !TAB ? 8 : 1];
       if constexpr (!TAB) {
@@ -1197,20 +1217,12 @@ __global__ void __launch_bounds__(128, TAB ? (POLICY ? 4 : 5) : (POLICY ? 3 : 4)
           if (POLICY && !TAB) ptv[j] = fma(xa.x, th_a0, xa.y * th_a1) + fma(xb.x, th_b0, xb.y * th_b1);
         }
       }
-      // table form: lane q fetches day q of the chunk -- the env's 8 days are one contiguous 128-byte run
-      double2 z_tab = make_double2(0.0, 0.0);
-      double pt_tab = 0.0;
-      if constexpr (TAB) {
-        const int dq = min(t + q, n_days - 1);
-        z_tab = __ldg(zt_env + dq);
-        if (POLICY) pt_tab = __ldg(p.tb.pt + row0 + dq);
-      }
       unsigned actm = 0, refm = 0;
       if (!POLICY) {
         // ---- this chunk's 8 action bits: lane q fetches day q's ------------------------------
         int a_mine = 0;
         if (q < nv) {
-          if (p.actions) a_mine = __ldg(p.actions + static_cast<size_t>(k + q) * p.n + e) != 0;
+          if (p.actions) a_mine = TAB ? (a_tab != 0) : (__ldg(p.actions + static_cast<size_t>(k + q) * p.n + e) != 0);
           else a_mine = rollout_hash(p.seed, static_cast<unsigned>(e), static_cast<unsigned>(k + q)) < p.threshold;
         }
         const unsigned am = (__ballot_sync(kFull, a_mine) >> (8 * g)) & 0xffu;
