@@ -21,10 +21,13 @@
 
 namespace {
 
-// below this the thread-per-env kernel is used by W2A_STEP_AUTO (B200: at 4 096 envs the
-// cooperative kernel already takes 5.2 us per step against 9.6 us, profiles/r01)
-constexpr int kHostStreams = 3;
-constexpr int64_t kHostChunk = 1 << 16;  // envs per pipelined chunk of the *_host calls
+constexpr int kHostStreams = 3;  // streams of the *_host pipeline (H2D / kernel / D2H of consecutive chunks overlap)
+int64_t g_host_chunk = 0;  // envs per pipelined chunk of the *_host calls; 0 = by env-set size (W2A_HOST_CHUNK overrides: tuning)
+// a quarter of the env set, between 2^16 (enough to hide the per-copy set-up) and 2^18 envs (B200: 0.93 -> 0.95 of the link at 2^20 envs)
+inline int64_t host_chunk(int64_t n) {
+  if (g_host_chunk > 0) return g_host_chunk;
+  return std::min<int64_t>(1 << 18, std::max<int64_t>(1 << 16, (n / 4) & ~int64_t{1023}));
+}
 
 struct HostEnvs {
   int64_t n = 0;
@@ -274,6 +277,7 @@ int w2a_create(int device, w2a_ctx** out) {
   const char* pdl_env = std::getenv("W2A_PDL");  // tuning switch: W2A_PDL=0 launches the step kernels fully serialised
   ctx->pdl = !(pdl_env && pdl_env[0] == '0');
   if (const char* ks = std::getenv("W2A_KEEP_STATE_MAX")) ctx->keep_state_max_envs = std::atoll(ks);
+  if (const char* hc = std::getenv("W2A_HOST_CHUNK")) g_host_chunk = std::max<int64_t>(1024, std::atoll(hc));
   *out = ctx;
   return W2A_OK;
 }
@@ -556,8 +560,9 @@ int w2a_reset_host(w2a_ctx* ctx, const int32_t* loc, const int32_t* year, const 
     }
   }
   int ci = 0;
-  for (int64_t c0 = 0; c0 < n; c0 += kHostChunk, ++ci) {
-    const int64_t m = std::min(kHostChunk, n - c0);
+  const int64_t chunk = host_chunk(n);
+  for (int64_t c0 = 0; c0 < n; c0 += chunk, ++ci) {
+    const int64_t m = std::min(chunk, n - c0);
     const size_t um = static_cast<size_t>(m);
     cudaStream_t st = h->streams[ci % kHostStreams];
     int32_t* d_loc = h->idx + c0;
@@ -617,8 +622,9 @@ int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward
     return W2A_OK;
   }
   int ci = 0;
-  for (int64_t c0 = 0; c0 < n; c0 += kHostChunk, ++ci) {
-    const int64_t m = std::min(kHostChunk, n - c0);
+  const int64_t chunk = host_chunk(n);
+  for (int64_t c0 = 0; c0 < n; c0 += chunk, ++ci) {
+    const int64_t m = std::min(chunk, n - c0);
     const size_t um = static_cast<size_t>(m);
     cudaStream_t st = h->streams[ci % kHostStreams];
     W2A_CUDA(ctx, cudaMemcpyAsync(h->action + c0, action + c0, um, cudaMemcpyHostToDevice, st));
