@@ -1226,17 +1226,16 @@ __global__ void __launch_bounds__(128, TAB ? (POLICY ? 4 : 5) : (POLICY ? 3 : 4)
           else a_mine = rollout_hash(p.seed, static_cast<unsigned>(e), static_cast<unsigned>(k + q)) < p.threshold;
         }
         const unsigned am = (__ballot_sync(kFull, a_mine) >> (8 * g)) & 0xffu;
-        // ---- integer recurrence of the chunk (env.py:242-250), replayed by every lane -----------
-        int r = rem;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const unsigned a = (am >> j) & 1u;
-          const unsigned atb = (r == 0) ? 1u : 0u;
-          const unsigned act = a & ~atb;
-          r -= static_cast<int>(act);
-          actm |= act << j;
-          refm |= (a & atb) << j;
+        // ---- integer recurrence of the chunk (env.py:242-250) in closed form ----------------------
+        // `at_budget = (remaining == 0)` refuses every alert once a POSITIVE budget has run out and never fires for a
+        // negative one: the accepted alerts are the first `rem` requested ones (all of them when rem < 0 or enough is left)
+        unsigned over = 0u;
+        if (rem >= 0 && rem < __popc(am)) {
+          over = am;
+          for (int i = 0; i < rem; ++i) over &= over - 1u;  // drop the `rem` earliest requests: what is left is refused
         }
+        actm = am & ~over;
+        refm = over;
       } else {
         // ---- the policy's table logits of the chunk's rows, one per lane, then known to every lane ----
         double t2[2] = {pt_tab, 0.0};
