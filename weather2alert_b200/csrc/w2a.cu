@@ -74,6 +74,7 @@ struct w2a_ctx {
   void* table_scratch = nullptr;  // z32_all | zt_all | x32 | pt, owned by the context (w2a_precompute_logits)
   std::vector<int32_t> col_to_loc_host;  // host copy of the county map (canonical check of the *_host resets)
   int64_t keep_state_max_envs = 3 << 19;  // W2A_KEEP_STATE_MAX overrides (0 = never)
+  int small_table_groups_per_sm = 16;  // TABLE step: env sets of up to this many 32-env groups per SM take the one-warp-per-CTA instance (W2A_SMALL_TABLE overrides, 0 = never)
   bool pdl = true;                // step kernels are launched with programmatic stream serialization (W2A_PDL=0: off)
   const void* occ_key[kMaxKernels] = {};  // occupancy (CTAs per SM) of each kernel launched so far
   int occ_val[kMaxKernels] = {};
@@ -149,7 +150,15 @@ int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int varia
     constexpr int kBlock = 32 * w2a::kTableWarps;
     int rc = grid_for(ctx, w2a::step_table_kernel<ADT>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);
     if (rc) return rc;
-    W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT>, grid, kBlock, w2a::kTableSmemBytes, st, ctx->pdl, a));
+    // small env sets (a step is a chain of memory latencies, not bandwidth): one warp per CTA so that the groups spread
+    // over the SMs, and all eight row gathers of a group in flight together
+    const int64_t groups = (static_cast<int64_t>(a.n) + 31) / 32;
+    if (groups <= static_cast<int64_t>(ctx->small_table_groups_per_sm) * ctx->sm_count) {
+      W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT, 8>, static_cast<int>(groups), 32,
+                                  sizeof(w2a::TableScratchWarp), st, ctx->pdl, a));
+    } else {
+      W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT>, grid, kBlock, w2a::kTableSmemBytes, st, ctx->pdl, a));
+    }
   } else if (variant == W2A_STEP_THREAD) {
     int rc = grid_for(ctx, w2a::step_thread_kernel<ADT>, 128, 0, 128, a.n, &grid);
     if (rc) return rc;
@@ -277,6 +286,7 @@ int w2a_create(int device, w2a_ctx** out) {
   const char* pdl_env = std::getenv("W2A_PDL");  // tuning switch: W2A_PDL=0 launches the step kernels fully serialised
   ctx->pdl = !(pdl_env && pdl_env[0] == '0');
   if (const char* ks = std::getenv("W2A_KEEP_STATE_MAX")) ctx->keep_state_max_envs = std::atoll(ks);
+  if (const char* sm = std::getenv("W2A_SMALL_TABLE")) ctx->small_table_groups_per_sm = std::atoi(sm);
   if (const char* hc = std::getenv("W2A_HOST_CHUNK")) g_host_chunk = std::max<int64_t>(1024, std::atoll(hc));
   *out = ctx;
   return W2A_OK;

@@ -757,8 +757,10 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #endif               // 2 sector gather from entry 0, 4 row gather from row 0, 8 no reward / flag outputs, 16 sectors of day 0
                      // whatever the day (the slice stays in L2), 64 / 128 the sector gather with 4 / 1 distinct lines per load
 
-template <int ADT>
-__global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_table_kernel(const StepArgs p) {
+// ROWS = rounds of row gathers in flight per warp: W2A_TABLE_ROWS for the bandwidth-bound sizes; 8 (every gather of the
+// group issued before anything waits) for env sets of a few groups per SM, where a step is a chain of memory latencies.
+template <int ADT, int ROWS = W2A_TABLE_ROWS>
+__global__ void __launch_bounds__(32 * kTableWarps, ROWS == W2A_TABLE_ROWS ? W2A_TABLE_MINBLOCKS : 4) step_table_kernel(const StepArgs p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const stage = reinterpret_cast<TableScratchWarp*>(smem_raw)[threadIdx.x >> 5].obs;
   const int lane = threadIdx.x & 31;
@@ -836,10 +838,10 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
 #else
     const float4 o0 = __ldg(zrec), o1 = __ldg(zrec + 1);
 #endif
-    float4 rows[W2A_TABLE_ROWS];  // observation rows: 8 lanes copy one float32 row, four neighbouring envs per round
+    float4 rows[ROWS];  // observation rows: 8 lanes copy one float32 row, four neighbouring envs per round
     auto load_rows = [&](int first) {
 #pragma unroll
-      for (int it = 0; it < W2A_TABLE_ROWS; ++it) {
+      for (int it = 0; it < ROWS; ++it) {
         const int j = 4 * (first + it) + g;
         const unsigned rowj = (W2A_KNOCK & 4) ? 0u : __shfl_sync(kFull, tr.row, j);
         rows[it] = __ldg(x32_lane + static_cast<size_t>(rowj) * 8);
@@ -847,7 +849,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
     };
     auto stage_rows = [&](int first) {
 #pragma unroll
-      for (int it = 0; it < W2A_TABLE_ROWS; ++it) {
+      for (int it = 0; it < ROWS; ++it) {
         const int j = 4 * (first + it) + g;
         float* st = stage + j * kObsDim + 4 * q;
         st[0] = rows[it].x;
@@ -923,7 +925,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_TABLE_MINBLOCKS) step_ta
       if (step_reward(zb, ze, tr.act) == 123.f) p.reward[e] = 0.f;  // keeps the arithmetic alive
     }
 #pragma unroll
-    for (int first = 0; first < 8; first += W2A_TABLE_ROWS) {
+    for (int first = 0; first < 8; first += ROWS) {
       if (first > 0) load_rows(first);
       stage_rows(first);
     }
