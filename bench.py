@@ -558,26 +558,34 @@ def run_ours(args):
                            "policy": "torch MLP 29-64-1 (fp32 matmuls) on the observation tensor, deterministic threshold",
                            "mode": "policy forward + step kernel x 153 + reset in one CUDA graph"}
             del roll
-            # the same network as ONE fused kernel per step (w2a_policy_mlp: tensor cores, float16 inputs, float32 accumulate)
-            venv.reset()
-            fused = venv.mlp_policy(pw1.T.contiguous(), torch.zeros(64, device=dev), pw2, 0.0)
-            roll = venv.graphed_rollout(fused, reset_at_end=True)
-            roll.replay()
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            p0.record()
-            for _ in range(3):
+            # the same network as ONE fused kernel per step (w2a_policy_mlp: tensor cores, float16 inputs, float32
+            # accumulate), then with the step and the policy in ONE launch per iteration (w2a_step_mlp)
+            for key, fuse, what, mode in (
+                    ("fused_mlp_policy", False,
+                     "the same 29-64-1 ReLU MLP as one w2a_policy_mlp launch per step (mma.sync f16 inputs, fp32 accumulate)",
+                     "policy kernel + step kernel x 153 + reset in one CUDA graph"),
+                    ("fused_step_and_policy", True,
+                     "the same MLP evaluated inside the step launch on the fresh observation rows (w2a_step_mlp)",
+                     "ONE kernel per iteration x 153 + reset in one CUDA graph; observations written, never read back")):
+                venv.reset()
+                fused = venv.mlp_policy(pw1.T.contiguous(), torch.zeros(64, device=dev), pw2, 0.0)
+                fused.fuse_step = fuse
+                roll = venv.graphed_rollout(fused, reset_at_end=True)
                 roll.replay()
-            p1.record()
-            torch.cuda.synchronize()
-            f_t = all_max(p0.elapsed_time(p1) / 3)
-            policy_info["fused_mlp_policy"] = {
-                "value": n * world * roll.steps / (f_t * 1e-3), "unit": UNIT, "ms_per_summer": f_t,
-                "us_per_step": f_t / roll.steps * 1e3,
-                "policy": "the same 29-64-1 ReLU MLP as one w2a_policy_mlp launch per step (mma.sync f16 inputs, fp32 accumulate)",
-                "mode": "policy kernel + step kernel x 153 + reset in one CUDA graph"}
-            del roll, venv
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                p0.record()
+                for _ in range(3):
+                    roll.replay()
+                p1.record()
+                torch.cuda.synchronize()
+                f_t = all_max(p0.elapsed_time(p1) / 3)
+                policy_info[key] = {
+                    "value": n * world * roll.steps / (f_t * 1e-3), "unit": UNIT, "ms_per_summer": f_t,
+                    "us_per_step": f_t / roll.steps * 1e3, "policy": what, "mode": mode}
+                del roll
+            del venv
         except Exception as exc:  # an extra: never let it take the headline line down
             policy_info = {"error": repr(exc)[:300]}
 

@@ -28,8 +28,8 @@
 extern "C" {
 #endif
 
-#define W2A_VERSION 200 /* 0.2.0: + w2a_precompute_logits (whole-summer tables; W2A_STEP_TABLE no longer builds per step),
-                           w2a_engineer_features, w2a_policy_mlp */
+#define W2A_VERSION 210 /* 0.2.0: + w2a_precompute_logits (whole-summer tables; W2A_STEP_TABLE no longer builds per step),
+                           w2a_engineer_features, w2a_policy_mlp; 0.2.1: + w2a_step_mlp */
 
 #define W2A_OK 0
 #define W2A_E_INVALID (-1)  /* bad argument (null pointer, size, dtype, variant) */
@@ -201,8 +201,9 @@ int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const d
  * policy in place of `action_space.sample()`): one launch computes
  *   logit = w2 . act(W1 . nan_to_num(obs) + b1) + b2,   action = logit > 0
  * (or, stochastic, action = hash(seed, env, step) < sigmoid(logit) * 2^32 -- the counter-based stream of w2a_rollout)
- * for n envs.  The 29 -> hidden contraction runs on the tensor cores with float16 inputs and float32 accumulation (obs and W1
- * are rounded to 11 significant bits; evaluate the policy the same way when training on these rollouts).
+ * for n envs.  Both layers run on the tensor cores with float16 inputs and float32 accumulation (obs, W1, b1, the hidden
+ * activations and w2 are rounded to 11 significant bits, values beyond +-65504 clamped; tanh is the hardware
+ * approximation, 2^-11 relative; evaluate the policy the same way when training on these rollouts).
  *   obs      dev float32 [n, 29]   (what w2a_step / w2a_reset wrote; NaN slots count as 0)
  *   w1       dev float32 [hidden, 29] row-major, b1 / w2 dev float32 [hidden]; hidden: multiple of 8, at most 64
  *   action   out dev uint8 [n];  logit  out dev float32 [n] or NULL */
@@ -211,6 +212,20 @@ int w2a_rollout_policy(w2a_ctx* ctx, void* stream, int64_t n, int steps, const d
 int w2a_policy_mlp(w2a_ctx* ctx, void* stream, int64_t n, const float* obs, const float* w1, const float* b1,
                    const float* w2, float b2, int hidden, int activation, int stochastic, uint64_t seed, uint32_t step,
                    uint8_t* action, float* logit);
+
+/* One iteration of that loop in ONE launch: the step of `action` (exactly w2a_step's outputs, `variant` as there) AND
+ * the policy's choice for the NEXT step, evaluated on the fresh observations while they are still on chip:
+ *   obs, reward, ... = step(action);   next_action = policy(obs)   [logit, ep_return += reward: optional]
+ * The observation tensor is written once and not read back, which the two-launch form (w2a_step, w2a_policy_mlp) pays
+ * for with 116 B per env through HBM.  With W2A_STEP_TABLE and the tables installed this is one kernel; any other
+ * variant runs as the separate launches, with identical results.  Actions are uint8; `next_action` may not alias `action`
+ * (alternate two buffers).  `step` numbers the policy's stochastic draw as in w2a_policy_mlp (the draw for the
+ * action that step k + 1 consumes).
+ *   ep_return  in/out dev float64 [n] or NULL */
+int w2a_step_mlp(w2a_ctx* ctx, void* stream, int64_t n, const uint8_t* action, void* state, float* obs, float* reward,
+                 uint8_t* terminated, int32_t* remaining, uint8_t* at_budget, int variant, const float* w1, const float* b1,
+                 const float* w2, float b2, int hidden, int activation, int stochastic, uint64_t seed, uint32_t step,
+                 uint8_t* next_action, float* logit, double* ep_return);
 
 /* ---- host-buffer entry points: the call a CPU-side RL loop makes ------------------
  * The context owns a device-resident env set; every call copies its inputs from and its

@@ -12,7 +12,8 @@ def _ref_logits(obs, w1, b1, w2, b2, activation):
     x = torch.nan_to_num(obs.double(), nan=0.0)
     pre = x @ w1.double().T + b1.double()
     hid = torch.relu(pre) if activation == "relu" else torch.tanh(pre)
-    mag = (x.abs() @ w1.double().abs().T) @ w2.double().abs()  # sum of |x w1| |w2|: what a 2^-11 relative rounding acts on
+    # sum of (|x w1| + |b1|) |w2|: what the 2^-11 relative roundings (inputs, weights, bias, hidden units, tanh) act on
+    mag = (x.abs() @ w1.double().abs().T + b1.double().abs()) @ w2.double().abs()
     return hid @ w2.double() + b2, mag
 
 
@@ -89,7 +90,67 @@ def test_mlp_policy_in_a_cuda_graph_equals_the_eager_loop():
         obs, r, term, _, _ = eager.step(a)
         ret += r
     assert bool(term.all()) and 0 < n_alerts < 153 * n
-    graphed = HeatAlertVectorEnv(n, **kw)
-    graphed.reset()
-    roll = graphed.graphed_rollout(graphed.mlp_policy(w1, b1, w2, 0.05, activation="tanh"), reset_at_end=True)
-    assert torch.equal(roll.replay(), ret)
+    # captured: step + policy as ONE launch per iteration (w2a_step_mlp, the default), and as two launches
+    for fuse in (True, False):
+        graphed = HeatAlertVectorEnv(n, **kw)
+        graphed.reset()
+        gpol = graphed.mlp_policy(w1, b1, w2, 0.05, activation="tanh")
+        gpol.fuse_step = fuse
+        before = graphed.core.launch_count
+        roll = graphed.graphed_rollout(gpol, reset_at_end=True)
+        assert torch.equal(roll.replay(), ret), fuse
+        assert torch.equal(gpol.logits, pol.logits) or fuse  # fused: one policy evaluation further (the terminal rows)
+        del roll
+    assert before > 0
+
+
+@pytest.mark.parametrize("H,activation,stochastic", [(64, "relu", False), (16, "tanh", True), (40, "relu", True)])
+def test_step_mlp_is_step_then_policy(golden, H, activation, stochastic):
+    """`w2a_step_mlp` (one launch: the step of action k and the policy's action k + 1 from the fresh rows on chip) against
+    `w2a_step` followed by `w2a_policy_mlp`, with the whole-summer tables (TABLE: the fused kernel) and without (COOP:
+    the library's own two-launch form) -- observations, rewards, flags, next actions, logits and return sums identical."""
+    from weather2alert_b200 import _lib
+    from weather2alert_b200.core import HeatAlertCore
+
+    store, weights = golden.store(), golden.weights("std")
+    for tables in (True, False):
+        core = HeatAlertCore(store, weights, "cuda:0", precompute=tables)
+        assert core.has_tables == tables
+        n = 20011 if tables else 3001
+        rng = np.random.default_rng(5)
+        col = rng.integers(0, len(weights.fips_list), n)  # every env on its own county's column: the tabulated path
+        idx = {k: torch.from_numpy(np.asarray(v).astype(np.int32)).cuda() for k, v in dict(
+            loc=[store.fips_index[weights.fips_list[c]] for c in col], year=rng.integers(0, store.shape[1], n),
+            coef_col=col, coef_idx=rng.integers(0, weights.n_samples, n)).items()}
+        g = torch.Generator(device="cuda").manual_seed(H)
+        w1 = torch.randn(H, 29, generator=g, device="cuda") * 0.3
+        w1[:, 17] *= 0.02
+        b1, w2 = torch.randn(H, generator=g, device="cuda") * 0.1, torch.randn(H, generator=g, device="cuda") * 0.5
+        kw = dict(activation=activation, stochastic=stochastic, seed=9)
+        variant = _lib.STEP_TABLE if tables else _lib.STEP_COOP
+
+        def buffers():
+            st, ob = core.alloc_state(n), torch.zeros((n, 29), device="cuda")
+            core.reset(st, ob, idx["loc"], idx["year"], idx["coef_col"], idx["coef_idx"])
+            return dict(state=st, obs=ob, reward=torch.zeros(n, device="cuda"), term=torch.zeros(n, dtype=torch.uint8, device="cuda"),
+                        rem=torch.zeros(n, dtype=torch.int32, device="cuda"), atb=torch.zeros(n, dtype=torch.uint8, device="cuda"),
+                        a=[torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(2)], logit=torch.zeros(n, device="cuda"),
+                        ret=torch.zeros(n, dtype=torch.float64, device="cuda"))
+
+        one, two = buffers(), buffers()
+        for b in (one, two):
+            core.policy_mlp(b["obs"], w1, b1, w2, -0.2, b["a"][0], logit=b["logit"], step=0, **kw)
+        for k in range(12):
+            cur, nxt = k & 1, (k + 1) & 1
+            core.step_mlp(one["state"], one["a"][cur], one["obs"], one["reward"], one["term"], one["rem"], one["atb"], w1, b1, w2,
+                          -0.2, one["a"][nxt], logit=one["logit"], ep_return=one["ret"], step=k + 1, variant=variant, **kw)
+            core.step(two["state"], two["a"][cur], two["obs"], two["reward"], two["term"], two["rem"], two["atb"], variant=variant)
+            two["ret"] += two["reward"]
+            core.policy_mlp(two["obs"], w1, b1, w2, -0.2, two["a"][nxt], logit=two["logit"], step=k + 1, **kw)
+            for key in ("state", "obs", "reward", "term", "rem", "atb", "logit", "ret"):
+                assert torch.equal(one[key].view(torch.uint8), two[key].view(torch.uint8)), (tables, k, key)
+            assert torch.equal(one["a"][nxt], two["a"][nxt]), (tables, k)
+        assert 0 < int(one["a"][0].sum()) < n
+    with pytest.raises(ValueError, match="alias"):
+        core.step_mlp(one["state"], one["a"][0], one["obs"], one["reward"], one["term"], one["rem"], one["atb"], w1, b1, w2, 0.0,
+                      one["a"][0])

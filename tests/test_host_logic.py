@@ -137,7 +137,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()  # ImportError if the extension was not built
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.w2a_version() == 200
+    assert lib.w2a_version() == 210
     assert lib.w2a_state_bytes(10) == 160
     # error paths that need no GPU
     assert lib.w2a_create(0, None) == -1

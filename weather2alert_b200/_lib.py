@@ -44,6 +44,8 @@ SIGNATURES = {
     "w2a_engineer_features": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "w2a_policy_mlp": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_uint64,
                                  C.c_uint32, _P, _P]),
+    "w2a_step_mlp": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_float, C.c_int, C.c_int,
+                               C.c_int, C.c_uint64, C.c_uint32, _P, _P, _P]),
     "w2a_launch_count": (C.c_int64, [_P]),
 }
 

@@ -206,6 +206,36 @@ class HeatAlertCore:
                                             H, act, int(bool(stochastic)), int(seed) & (2**64 - 1), int(step) & 0xFFFFFFFF,
                                             _ptr(action), _ptr(logit)), self.ctx)
 
+    def step_mlp(self, state, action, obs, reward, terminated, remaining, at_budget, w1, b1, w2, b2: float, next_action,
+                 logit=None, ep_return=None, activation: str = "relu", stochastic: bool = False, seed: int = 0, step: int = 0,
+                 variant: int | None = None):
+        """One iteration of `a = policy(obs); env.step(a)` in one launch (`w2a_step_mlp`): the step of `action` and the
+        MLP policy's `next_action` from the fresh observations, which are written but never read back.  Arguments as
+        in `step` / `policy_mlp`; `ep_return` (float64 [n], optional) accumulates the rewards."""
+        n = action.numel()
+        H = b1.numel()
+        if variant is None:
+            variant = _lib.STEP_TABLE if self.has_tables else _lib.STEP_COOP
+        self._check_dev("action", action, torch.uint8, n)
+        self._check_dev("next_action", next_action, torch.uint8, n)
+        if action.data_ptr() == next_action.data_ptr():
+            raise ValueError("step_mlp: next_action must not alias action")
+        self._check_dev("obs", obs, torch.float32, n * _lib.OBS_DIM)
+        self._check_dev("reward", reward, torch.float32, n)
+        self._check_dev("terminated", terminated, (torch.uint8, torch.bool), n)
+        self._check_dev("remaining", remaining, torch.int32, n)
+        self._check_dev("at_budget", at_budget, (torch.uint8, torch.bool), n)
+        self._check_dev("w1", w1, torch.float32, H * _lib.OBS_DIM)
+        self._check_dev("b1", b1, torch.float32, H)
+        self._check_dev("w2", w2, torch.float32, H)
+        self._check_dev("logit", logit, torch.float32, n)
+        self._check_dev("ep_return", ep_return, torch.float64, n)
+        act = {"relu": 0, "tanh": 1}[activation]
+        _lib.check(self._lib.w2a_step_mlp(self.ctx, self._stream(), n, _ptr(action), _ptr(state), _ptr(obs), _ptr(reward),
+                                          _ptr(terminated), _ptr(remaining), _ptr(at_budget), int(variant), _ptr(w1), _ptr(b1),
+                                          _ptr(w2), float(b2), H, act, int(bool(stochastic)), int(seed) & (2**64 - 1),
+                                          int(step) & 0xFFFFFFFF, _ptr(next_action), _ptr(logit), _ptr(ep_return)), self.ctx)
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.w2a_launch_count(self.ctx))

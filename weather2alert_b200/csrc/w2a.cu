@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "w2a_features.cuh"
@@ -59,7 +60,7 @@ struct HostEnvs {
 constexpr int64_t kHostPackedMax = 1024;
 
 char g_create_error[512] = "";
-constexpr int kMaxKernels = 16;
+constexpr int kMaxKernels = 32;
 
 }  // namespace
 
@@ -777,38 +778,129 @@ int w2a_engineer_features(w2a_ctx* ctx, void* stream, int64_t n_rows, int n_coun
   return W2A_OK;
 }
 
+}  // extern "C"
+
+namespace {
+int fill_policy_args(w2a_ctx* ctx, const char* who, int64_t n, const float* obs, const float* w1, const float* b1, const float* w2,
+                     float b2, int hidden, int activation, int stochastic, uint64_t seed, uint32_t step, uint8_t* action,
+                     float* logit, w2a::PolicyMlpArgs* a) {
+  if (n < 0 || n >= (int64_t{1} << 31) - 64 || !obs || !w1 || !b1 || !w2 || !action)
+    return fail(ctx, W2A_E_INVALID, "%s: NULL argument or n out of range", who);
+  if (hidden < 8 || hidden > w2a::kPolMaxHidden || (hidden & 7))
+    return fail(ctx, W2A_E_INVALID, "%s: hidden=%d must be a multiple of 8 in [8, %d]", who, hidden, w2a::kPolMaxHidden);
+  if (activation != W2A_ACT_RELU && activation != W2A_ACT_TANH)
+    return fail(ctx, W2A_E_INVALID, "%s: unknown activation %d", who, activation);
+  a->obs = obs;
+  a->w1 = w1;
+  a->b1 = b1;
+  a->w2 = w2;
+  a->b2 = b2;
+  a->hidden = hidden;
+  a->activation = activation;
+  a->stochastic = stochastic != 0;
+  a->seed = seed;
+  a->step = step;
+  a->action = action;
+  a->logit = logit;
+  a->n = static_cast<int>(n);
+  return W2A_OK;
+}
+
+// one instance per (hidden size rounded up to 16 / 32 / 64, activation): the tile loops unroll at compile time
+template <typename F>
+int by_policy_shape(int hidden, int activation, F&& go) {
+  const int nt = hidden <= 16 ? 2 : hidden <= 32 ? 4 : 8;
+  if (activation == W2A_ACT_RELU) {
+    if (nt == 2) return go(std::integral_constant<int, 2>{}, std::integral_constant<int, 0>{});
+    if (nt == 4) return go(std::integral_constant<int, 4>{}, std::integral_constant<int, 0>{});
+    return go(std::integral_constant<int, 8>{}, std::integral_constant<int, 0>{});
+  }
+  if (nt == 2) return go(std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{});
+  if (nt == 4) return go(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{});
+  return go(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
+}
+
+int launch_policy(w2a_ctx* ctx, cudaStream_t st, const w2a::PolicyMlpArgs& a) {
+  constexpr int kBlock = 32 * w2a::kPolWarps;
+  const size_t smem = sizeof(w2a::PolicyScratch);
+  int rc = by_policy_shape(a.hidden, a.activation, [&](auto nt, auto act) -> int {
+    auto kernel = w2a::policy_mlp_kernel<decltype(nt)::value, decltype(act)::value>;
+    int grid = 0;
+    int rc2 = grid_for(ctx, kernel, kBlock, smem, kBlock, a.n, &grid);
+    if (rc2) return rc2;
+    W2A_CUDA(ctx, launch_kernel(kernel, grid, kBlock, smem, st, ctx->pdl, a));
+    return W2A_OK;
+  });
+  if (rc) return rc;
+  ctx->launches++;
+  W2A_CUDA(ctx, cudaGetLastError());
+  return W2A_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int w2a_policy_mlp(w2a_ctx* ctx, void* stream, int64_t n, const float* obs, const float* w1, const float* b1,
                    const float* w2, float b2, int hidden, int activation, int stochastic, uint64_t seed, uint32_t step,
                    uint8_t* action, float* logit) {
   if (!ctx) return W2A_E_INVALID;
   if (n == 0) return W2A_OK;
-  if (n < 0 || n >= (int64_t{1} << 31) - 64 || !obs || !w1 || !b1 || !w2 || !action)
-    return fail(ctx, W2A_E_INVALID, "w2a_policy_mlp: NULL argument or n out of range");
-  if (hidden < 8 || hidden > w2a::kPolMaxHidden || (hidden & 7))
-    return fail(ctx, W2A_E_INVALID, "w2a_policy_mlp: hidden=%d must be a multiple of 8 in [8, %d]", hidden, w2a::kPolMaxHidden);
-  if (activation != W2A_ACT_RELU && activation != W2A_ACT_TANH)
-    return fail(ctx, W2A_E_INVALID, "w2a_policy_mlp: unknown activation %d", activation);
-  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
   w2a::PolicyMlpArgs a;
-  a.obs = obs;
-  a.w1 = w1;
-  a.b1 = b1;
-  a.w2 = w2;
-  a.b2 = b2;
-  a.hidden = hidden;
-  a.activation = activation;
-  a.stochastic = stochastic != 0;
-  a.seed = seed;
-  a.step = step;
-  a.action = action;
-  a.logit = logit;
-  a.n = static_cast<int>(n);
-  constexpr int kBlock = 32 * w2a::kPolWarps;
-  const size_t smem = sizeof(w2a::PolicyScratch);
-  int grid = 0;
-  int rc = grid_for(ctx, w2a::policy_mlp_kernel, kBlock, smem, kBlock, n, &grid);
+  int rc = fill_policy_args(ctx, "w2a_policy_mlp", n, obs, w1, b1, w2, b2, hidden, activation, stochastic, seed, step, action,
+                            logit, &a);
   if (rc) return rc;
-  W2A_CUDA(ctx, launch_kernel(w2a::policy_mlp_kernel, grid, kBlock, smem, static_cast<cudaStream_t>(stream), ctx->pdl, a));
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  return launch_policy(ctx, static_cast<cudaStream_t>(stream), a);
+}
+
+int w2a_step_mlp(w2a_ctx* ctx, void* stream, int64_t n, const uint8_t* action, void* state, float* obs, float* reward,
+                 uint8_t* terminated, int32_t* remaining, uint8_t* at_budget, int variant, const float* w1, const float* b1,
+                 const float* w2, float b2, int hidden, int activation, int stochastic, uint64_t seed, uint32_t step,
+                 uint8_t* next_action, float* logit, double* ep_return) {
+  int rc = check_ready(ctx, "w2a_step_mlp", n);
+  if (rc) return rc;
+  if (n == 0) return W2A_OK;
+  if (!action || !state || !obs || !reward || !terminated) return fail(ctx, W2A_E_INVALID, "w2a_step_mlp: NULL argument");
+  w2a::PolicyMlpArgs m;
+  rc = fill_policy_args(ctx, "w2a_step_mlp", n, obs, w1, b1, w2, b2, hidden, activation, stochastic, seed, step, next_action,
+                        logit, &m);
+  if (rc) return rc;
+  W2A_CUDA(ctx, cudaSetDevice(ctx->device));
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (variant != W2A_STEP_TABLE || !ctx->tb.z32_all) {
+    // no tables (or another variant asked for): the same result from two launches, and the return sum from a third
+    rc = step_planes(ctx, st, n, action, W2A_ACT_U8, plane_static(state), plane_mut(state, n), obs, reward, terminated, remaining,
+                     at_budget, variant);
+    if (rc) return rc;
+    if (ep_return) {
+      w2a::add_rewards_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, ctx->sm_count * 8)), 256, 0, st>>>(
+          reward, ep_return, static_cast<int>(n));
+      ctx->launches++;
+    }
+    return launch_policy(ctx, st, m);
+  }
+  w2a::StepArgs a;
+  a.tb = ctx->tb;
+  a.st_static = plane_static(state);
+  a.st_mut = plane_mut(state, n);
+  a.action = action;
+  a.obs = obs;
+  a.reward = reward;
+  a.terminated = terminated;
+  a.remaining = remaining;
+  a.at_budget = at_budget;
+  a.n = static_cast<int>(n);
+  a.keep_state = n <= ctx->keep_state_max_envs ? 1 : 0;
+  constexpr int kBlock = 32 * w2a::kTableWarps;
+  rc = by_policy_shape(hidden, activation, [&](auto nt, auto act) -> int {
+    auto kernel = w2a::step_mlp_kernel<0, decltype(nt)::value, decltype(act)::value>;
+    int grid = 0;
+    int rc2 = grid_for(ctx, kernel, kBlock, w2a::kStepMlpSmemBytes, kBlock, n, &grid);
+    if (rc2) return rc2;
+    W2A_CUDA(ctx, launch_kernel(kernel, grid, kBlock, w2a::kStepMlpSmemBytes, st, ctx->pdl, a, m, ep_return));
+    return W2A_OK;
+  });
+  if (rc) return rc;
   ctx->launches++;
   W2A_CUDA(ctx, cudaGetLastError());
   return W2A_OK;

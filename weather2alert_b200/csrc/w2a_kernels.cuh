@@ -759,8 +759,14 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 
 // ROWS = rounds of row gathers in flight per warp: W2A_TABLE_ROWS for the bandwidth-bound sizes; 8 (every gather of the
 // group issued before anything waits) for env sets of a few groups per SM, where a step is a chain of memory latencies.
-template <int ADT, int ROWS = W2A_TABLE_ROWS>
-__global__ void __launch_bounds__(32 * kTableWarps, ROWS == W2A_TABLE_ROWS ? W2A_TABLE_MINBLOCKS : 4) step_table_kernel(const StepArgs p) {
+// `post` hooks a consumer of the fresh observations into the kernel (w2a_policy.cuh: the MLP policy that picks the next
+// action from the rows while they are still in shared memory); StepNoPost is the plain step.
+struct StepNoPost {
+  __device__ __forceinline__ void reward(int, float) const {}
+  __device__ __forceinline__ void group(const float*, int, int) const {}
+};
+template <int ADT, int ROWS, typename Post>
+__device__ __forceinline__ void step_table_body(const StepArgs& p, Post& post) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const stage = reinterpret_cast<TableScratchWarp*>(smem_raw)[threadIdx.x >> 5].obs;
   const int lane = threadIdx.x & 31;
@@ -917,7 +923,9 @@ __global__ void __launch_bounds__(32 * kTableWarps, ROWS == W2A_TABLE_ROWS ? W2A
       ze += ae;
     }
     if (valid && !(W2A_KNOCK & 8)) {
-      __stcs(p.reward + e, step_reward(zb, ze, tr.act));
+      const float r = step_reward(zb, ze, tr.act);
+      __stcs(p.reward + e, r);
+      post.reward(e, r);
       p.terminated[e] = static_cast<uint8_t>(tr.done);
       if (p.remaining) __stcs(p.remaining + e, tr.rem);
       if (p.at_budget) p.at_budget[e] = static_cast<uint8_t>(tr.at_budget);
@@ -948,9 +956,16 @@ __global__ void __launch_bounds__(32 * kTableWarps, ROWS == W2A_TABLE_ROWS ? W2A
         if ((wmask >> env) & 1u) st_stream(ob + i, stage[i]);
       }
     }
+    post.group(stage, base, min(32, p.n - base));  // the group's 32 rows as the observation tensor holds them
     __syncwarp();
   }
   if (bulk_pending && lane == 0) bulk_store_wait_all();
+}
+
+template <int ADT, int ROWS = W2A_TABLE_ROWS>
+__global__ void __launch_bounds__(32 * kTableWarps, ROWS == W2A_TABLE_ROWS ? W2A_TABLE_MINBLOCKS : 4) step_table_kernel(const StepArgs p) {
+  StepNoPost post;
+  step_table_body<ADT, ROWS>(p, post);
 }
 
 // =========================================================================================

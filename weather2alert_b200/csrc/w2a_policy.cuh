@@ -11,9 +11,10 @@
 // x 2 k-steps).  The op reads 116 B and does ~4 kFLOP per env (intensity 35 FLOP/B against a ridge of ~210), so the
 // tensor pipe idles most of the time by construction -- the point of using it is to get the 1 900 multiply-adds per
 // env off the FP32 pipe (56 us per 2^20 envs there), not to approach its peak; a tcgen05/TMEM pipeline would buy
-// nothing here.  Inputs and weights are rounded to float16 (11 significant bits, the precision of TF32; observation
-// slots stay far below its range): logits agree with a float32 evaluation to ~1e-3 of the summed |x.w| magnitudes;
-// an agent that trains on these rollouts should evaluate its policy the same way.
+// nothing here.  Inputs, weights, bias and hidden activations are rounded to float16 (11 significant bits, the
+// precision of TF32; values beyond its range are clamped to +-65504) and the second layer runs on the tensor cores as
+// well, straight from the first layer's accumulator registers: logits agree with a float32 evaluation to ~1e-3 of the
+// summed |x.w| magnitudes; an agent that trains on these rollouts should evaluate its policy the same way.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -42,10 +43,28 @@ struct PolicyMlpArgs {
   int n;
 };
 
+// two float32 -> one register of two float16 (first argument in the low half), clamped to the finite float16 range
 __device__ __forceinline__ unsigned pack_half2(float lo, float hi) {
   unsigned r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
   return r;
+}
+// the same with max(x, 0) applied first: relu, rounding and packing of two hidden units in ONE instruction (F2FP.RELU)
+__device__ __forceinline__ unsigned pack_half2_relu(float lo, float hi) {
+  unsigned r;
+  asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float tanh_approx(float x) {  // MUFU.TANH: 2^-11 relative, the precision of the float16 operands
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// nan_to_num on a packed pair: a half that is NaN becomes 0 (the significance slot is NaN when there is no alert)
+__device__ __forceinline__ unsigned zero_nan_half2(unsigned v) {
+  unsigned m;
+  asm("set.eq.u32.f16x2 %0, %1, %1;" : "=r"(m) : "r"(v));  // 0xffff per half that equals itself
+  return v & m;
 }
 // D(16x8) += A(16x16) * B(16x8), float16 inputs (two per register), float32 accumulate.
 // A: a0 = [gid][2tig, 2tig+1], a1 = [gid+8][...], a2 = [gid][2tig+8, +9], a3 = [gid+8][2tig+8, +9];
@@ -57,39 +76,150 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const unsigned (&a)[4], u
 }
 
 constexpr int kPolWarps = 4;
+constexpr int kPolW1Words = kPolMaxHidden * kPolWStride;  // half2 words of the first layer in shared memory
 struct __align__(16) PolicyScratch {
-  unsigned w1[kPolMaxHidden * kPolWStride];  // half2 words, [h][k / 2], k >= 29 zero
-  float b1[kPolMaxHidden], w2[kPolMaxHidden];
+  unsigned w1[kPolW1Words];                    // [h][k / 2]: k < 29 the weights, k = 29 the bias b1[h], k >= 30 zero
   float rows[kPolWarps][2][32 * kObsDim + 4];  // per warp, double buffered: the 32 observation rows of a group, as in global memory
 };
 
-__global__ void __launch_bounds__(32 * kPolWarps, 4) policy_mlp_kernel(const PolicyMlpArgs p) {
+// NT = n-tiles of 8 hidden units (H rounded up to 16 / 32 / 64: units beyond H have zero weights and contribute 0),
+// ACT = 0 relu, 1 tanh.
+// First layer -> shared memory (float16 pairs, b1 as the weight of the constant-1 input in the padding column k = 29);
+// second layer -> this lane's B fragments of the [16 x 8] tiles whose column 0 is w2 (the other seven columns are zero).
+template <int NT>
+__device__ __forceinline__ void mlp_load_weights(const PolicyMlpArgs& p, unsigned* w1s, unsigned (&w2f)[NT / 2][2]) {
+  const int H = p.hidden;
+  const int gid = (threadIdx.x & 31) >> 2, tig = threadIdx.x & 3;
+  for (int i = threadIdx.x; i < 8 * NT * kPolWStride; i += blockDim.x) {
+    const int h = i / kPolWStride, k = 2 * (i - h * kPolWStride);
+    const float lo = (h < H && k < kObsDim) ? __ldg(p.w1 + h * kObsDim + k) : 0.f;
+    float hi = (h < H && k + 1 < kObsDim) ? __ldg(p.w1 + h * kObsDim + k + 1) : 0.f;
+    if (h < H && k + 1 == kObsDim) hi = __ldg(p.b1 + h);
+    w1s[i] = pack_half2(lo, hi);
+  }
+#pragma unroll
+  for (int u = 0; u < NT / 2; ++u) {
+    const int h0 = 16 * u + 2 * tig;
+    const float v0 = (gid == 0 && h0 < H) ? __ldg(p.w2 + h0) : 0.f, v1 = (gid == 0 && h0 + 1 < H) ? __ldg(p.w2 + h0 + 1) : 0.f;
+    const float v8 = (gid == 0 && h0 + 8 < H) ? __ldg(p.w2 + h0 + 8) : 0.f, v9 = (gid == 0 && h0 + 9 < H) ? __ldg(p.w2 + h0 + 9) : 0.f;
+    w2f[u][0] = pack_half2(v0, v1);
+    w2f[u][1] = pack_half2(v8, v9);
+  }
+}
+
+// The policy on one group of 32 envs whose observation rows lie in shared memory as in the observation tensor (row
+// stride 29 floats).  Per lane: 32 shared loads + 16 conversions for the A fragments, then per 16 hidden units 8
+// tensor-core instructions for the first layer, 4 conversions (activation included) and 2 more tensor-core instructions
+// for the second layer: the first layer's accumulator fragment of two neighbouring n-tiles IS the A fragment of a
+// 16 x 16 tile, so the hidden activations never leave the registers.
+// MT = m-tiles (16 envs each) per pass: 2 shares every first-layer B fragment between both halves of the group; 1 does
+// the halves one after the other with half the registers (the step kernel hosting the policy has few to spare).
+template <int NT, int ACT, int MT>
+__device__ __forceinline__ void mlp_group(const PolicyMlpArgs& p, const float* rows, const unsigned* w1s,
+                                          const unsigned (&w2f)[NT / 2][2], int base, int n_valid) {
+  const int lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int m0 = 0; m0 < 2; m0 += MT) {
+    // ---- A fragments: [MT m-tiles of 16 envs] x [2 k-steps of 16 slots] ------------------------------------------
+    unsigned a[MT][2][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float* el = rows + (16 * (m0 + m) + gid + 8 * (c & 1)) * kObsDim + 16 * ks + 2 * tig + 8 * (c >> 1);
+          float v0, v1;
+          if (ks == 1 && (c >> 1) == 1) {  // slots 24 + 2 tig: (24, 25) (26, 27) (28, bias input 1) (none)
+            v0 = tig < 3 ? el[0] : 0.f;
+            v1 = tig < 2 ? el[1] : (tig == 2 ? 1.f : 0.f);
+          } else {
+            v0 = el[0];
+            v1 = el[1];
+          }
+          a[m][ks][c] = zero_nan_half2(pack_half2(v0, v1));
+        }
+    // ---- 16 hidden units at a time: first layer, activation, second layer -- all in registers --------------------
+    float out[MT][4];  // column 0 of C = the logit of rows gid | gid + 8 of the m-tile
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) out[m][c] = 0.f;
+#pragma unroll
+    for (int u = 0; u < NT / 2; ++u) {
+      float acc[2][MT][4];  // [n-tile of the pair][m-tile]
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[jj][m][c] = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const unsigned* wrow = w1s + (8 * (2 * u + jj) + gid) * kPolWStride + 8 * ks + tig;
+          const unsigned b0 = wrow[0], b1 = wrow[4];
+#pragma unroll
+          for (int m = 0; m < MT; ++m) mma_f16(acc[jj][m], a[m][ks], b0, b1);
+        }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        unsigned hfrag[4];  // C layout of n-tiles (2u, 2u + 1) = A layout of the 16 x 16 tile of hidden units 16u .. 16u + 15
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float x0 = acc[c >> 1][m][2 * (c & 1)], x1 = acc[c >> 1][m][2 * (c & 1) + 1];
+          hfrag[c] = ACT == 0 ? pack_half2_relu(x0, x1) : pack_half2(tanh_approx(x0), tanh_approx(x1));
+        }
+        mma_f16(out[m], hfrag, w2f[u][0], w2f[u][1]);
+      }
+    }
+    if (tig == 0) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = 16 * (m0 + m) + gid + 8 * r;
+          const int e = base + row;
+          if (row < n_valid) {
+            const float z = out[m][2 * r] + p.b2;
+            unsigned act;
+            if (p.stochastic) {
+              const double thr = static_cast<double>(1.f / (1.f + __expf(-z))) * 4294967296.0;
+              const unsigned thr_u = thr >= 4294967295.0 ? 0xffffffffu : static_cast<unsigned>(thr);
+              act = rollout_hash(p.seed, static_cast<unsigned>(e), p.step) < thr_u ? 1u : 0u;
+            } else {
+              act = z > 0.f ? 1u : 0u;
+            }
+            p.action[e] = static_cast<uint8_t>(act);
+            if (p.logit) p.logit[e] = z;
+          }
+        }
+    }
+  }
+}
+
+template <int NT, int ACT>
+__global__ void __launch_bounds__(32 * kPolWarps, 5) policy_mlp_kernel(const PolicyMlpArgs p) {
   extern __shared__ __align__(16) unsigned char pol_smem[];
   PolicyScratch& s = *reinterpret_cast<PolicyScratch*>(pol_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gid = lane >> 2, tig = lane & 3;
-  const int H = p.hidden, ntiles = H >> 3;
-  for (int i = threadIdx.x; i < kPolMaxHidden * kPolWStride; i += blockDim.x) {
-    const int h = i / kPolWStride, k = 2 * (i - h * kPolWStride);
-    const float lo = (h < H && k < kObsDim) ? __ldg(p.w1 + h * kObsDim + k) : 0.f;
-    const float hi = (h < H && k + 1 < kObsDim) ? __ldg(p.w1 + h * kObsDim + k + 1) : 0.f;
-    s.w1[i] = pack_half2(lo, hi);
-  }
-  for (int i = threadIdx.x; i < kPolMaxHidden; i += blockDim.x) {
-    s.b1[i] = i < H ? __ldg(p.b1 + i) : 0.f;
-    s.w2[i] = i < H ? __ldg(p.w2 + i) : 0.f;
-  }
   pdl_launch_dependents();
-  pdl_wait();  // the observations come from the step launch before this one
+  pdl_wait();  // the observations come from the step launch before this one (and the weights may come from an optimiser's)
+  unsigned w2f[NT / 2][2];
+  mlp_load_weights<NT>(p, s.w1, w2f);
   __syncthreads();
   const int n_groups = (p.n + 31) >> 5;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const bool aligned = (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
-  // the rows of group `wg` -> buffer `b`: 32 x 116 contiguous bytes copied as they lie, asynchronously (cp.async, 16 B
+  // Groups are walked from the LAST one down: the step kernel that produced the observations wrote them in ascending
+  // order, so the tail of the buffer is what is still in L2 when this kernel starts.
+  // The rows of a group -> buffer `b`: 32 x 116 contiguous bytes copied as they lie, asynchronously (cp.async, 16 B
   // per lane and round) when the group is full, so that the next group's rows fly while this one is in the tensor cores
-  auto fetch_rows = [&](int wg, int b) {
-    if (wg >= n_groups) return;
-    const int base = wg << 5;
+  auto fetch_rows = [&](int it, int b) {
+    if (it >= n_groups) return;
+    const int base = (n_groups - 1 - it) << 5;
     const int n_valid = min(32, p.n - base);
     const float* src = p.obs + static_cast<size_t>(base) * kObsDim;
     float* dst = s.rows[warp][b];
@@ -107,95 +237,60 @@ __global__ void __launch_bounds__(32 * kPolWarps, 4) policy_mlp_kernel(const Pol
   fetch_rows(wg, 0);
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (; wg < n_groups; wg += warps_total, buf ^= 1) {
-    const int base = wg << 5;
-    const int n_valid = min(32, p.n - base);
+    const int base = (n_groups - 1 - wg) << 5;
     fetch_rows(wg + warps_total, buf ^ 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // this group's rows have landed; the next group's are in flight
     __syncwarp();
-    const float* const rows = s.rows[warp][buf];
-    // ---- hidden pre-activations: [32, 32] x [32, H] on the tensor cores -----------------------------------
-    float acc[2][kPolMaxHidden / 8][4];
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int j = 0; j < kPolMaxHidden / 8; ++j)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[m][j][c] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < kPolK / 16; ++ks) {
-      unsigned a[2][4];
-#pragma unroll
-      for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int r = 16 * m + gid + 8 * (c & 1), k = 16 * ks + 2 * tig + 8 * (c >> 1);
-          float v0 = k < kObsDim ? rows[r * kObsDim + k] : 0.f;
-          float v1 = k + 1 < kObsDim ? rows[r * kObsDim + k + 1] : 0.f;
-          v0 = v0 == v0 ? v0 : 0.f;  // nan_to_num: the significance slot is NaN when there is no alert
-          v1 = v1 == v1 ? v1 : 0.f;
-          a[m][c] = pack_half2(v0, v1);
-        }
-#pragma unroll
-      for (int j = 0; j < kPolMaxHidden / 8; ++j) {
-        if (j < ntiles) {
-          const unsigned* wrow = s.w1 + (8 * j + gid) * kPolWStride + 8 * ks + tig;
-          const unsigned b0 = wrow[0], b1 = wrow[4];
-          mma_f16(acc[0][j], a[0], b0, b1);
-          mma_f16(acc[1][j], a[1], b0, b1);
-        }
-      }
-    }
-    // ---- activation, output layer: every thread folds its columns, the four threads of a row then add up --------
-    float part[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // [m-tile][row gid | gid + 8]
-#pragma unroll
-    for (int j = 0; j < kPolMaxHidden / 8; ++j) {
-      if (j < ntiles) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int h = 8 * j + 2 * tig + (c & 1);
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            const float pre = acc[m][j][c] + s.b1[h];
-            const float hid = p.activation == 0 ? fmaxf(pre, 0.f) : tanhf(pre);
-            part[m][c >> 1] = fmaf(hid, s.w2[h], part[m][c >> 1]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        float v = part[m][r];
-        v += __shfl_xor_sync(kFull, v, 1);
-        v += __shfl_xor_sync(kFull, v, 2);
-        part[m][r] = v + p.b2;
-      }
-    if (tig == 0) {
-#pragma unroll
-      for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int row = 16 * m + gid + 8 * r;
-          const int e = base + row;
-          if (row < n_valid) {
-            const float z = part[m][r];
-            unsigned a;
-            if (p.stochastic) {
-              const double thr = static_cast<double>(1.f / (1.f + __expf(-z))) * 4294967296.0;
-              const unsigned thr_u = thr >= 4294967295.0 ? 0xffffffffu : static_cast<unsigned>(thr);
-              a = rollout_hash(p.seed, static_cast<unsigned>(e), p.step) < thr_u ? 1u : 0u;
-            } else {
-              a = z > 0.f ? 1u : 0u;
-            }
-            p.action[e] = static_cast<uint8_t>(a);
-            if (p.logit) p.logit[e] = z;
-          }
-        }
-    }
+    mlp_group<NT, ACT, 2>(p, s.rows[warp][buf], s.w1, w2f, base, min(32, p.n - base));
     __syncwarp();
   }
+}
+
+// ---- step + policy in ONE launch ---------------------------------------------------------------------------------
+// `a = policy(obs); obs = env.step(a)` step by step costs the observation tensor twice: 116 B per env written by the
+// step and read back by the policy, most of it through HBM (122 MB at 2^20 envs, about what L2 holds).  Here the TABLE
+// step's warp evaluates the policy on its 32 fresh rows while they sit in its staging buffer, on their way out: the
+// launch takes the actions of step k, writes observation, reward and flags of step k as the plain step does, AND the
+// policy's actions for step k + 1 -- the tensor-core work fills issue slots the memory-bound step leaves idle.
+#ifndef W2A_STEP_MLP_MT
+#define W2A_STEP_MLP_MT 1  // m-tiles of the policy per pass inside the step kernel (1: half the registers, occupancy matters more)
+#endif
+template <int NT, int ACT>
+struct StepMlpPost {
+  const PolicyMlpArgs& m;
+  double* ep_return;  // optional: += reward per env (the return of the rollout so far)
+  unsigned* w1s;
+  unsigned w2f[NT / 2][2];
+  __device__ __forceinline__ void reward(int e, float r) const {
+    // a reduction without a return value (RED.ADD.F64, done by L2): a load-add-store here would put a DRAM round trip
+    // into every group's critical path
+    if (ep_return) atomicAdd(ep_return + e, static_cast<double>(r));
+  }
+  __device__ __forceinline__ void group(const float* rows, int base, int n_valid) const {
+    mlp_group<NT, ACT, W2A_STEP_MLP_MT>(m, rows, w1s, w2f, base, n_valid);
+  }
+};
+// ep_return += reward, for the two-launch form of w2a_step_mlp
+__global__ void __launch_bounds__(256) add_rewards_kernel(const float* __restrict__ reward, double* __restrict__ ep_return, int n) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) ep_return[e] += static_cast<double>(reward[e]);
+}
+constexpr int kStepMlpSmemBytes = kTableSmemBytes + kPolW1Words * static_cast<int>(sizeof(unsigned));
+
+#ifndef W2A_STEP_MLP_MINBLOCKS
+#define W2A_STEP_MLP_MINBLOCKS 7  // x 4 warps at 72 registers (B200 sweep, us per iteration at 2^20 envs: 4: 64.1, 5: 59.4, 6: 58.2, 7: 57.8, 8: 58.0)
+#endif
+template <int ADT, int NT, int ACT>
+__global__ void __launch_bounds__(32 * kTableWarps, W2A_STEP_MLP_MINBLOCKS) step_mlp_kernel(const StepArgs p, const PolicyMlpArgs m, double* ep_return) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StepMlpPost<NT, ACT> post{m, ep_return, reinterpret_cast<unsigned*>(smem_raw + kTableSmemBytes), {}};
+  // the weights go to shared memory with every warp of the CTA present (the body retires warps that have no group),
+  // and after the wait: an optimiser's launch may have written them just before
+  pdl_launch_dependents();
+  pdl_wait();
+  mlp_load_weights<NT>(m, post.w1s, post.w2f);
+  __syncthreads();
+  step_table_body<ADT, W2A_TABLE_ROWS>(p, post);
 }
 
 }  // namespace w2a

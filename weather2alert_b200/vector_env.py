@@ -445,6 +445,11 @@ class HeatAlertVectorEnv(VectorEnv):
 
         policy.calls = 0
         policy.logits = logits
+        # what `graphed_rollout` needs to run step + policy as ONE launch per iteration (`w2a_step_mlp`); set
+        # `policy.fuse_step = False` to keep the two launches
+        policy.fuse_step = True
+        policy.mlp = dict(w1=w1_t, b1=b1_t, w2=w2_t, b2=float(b2), activation=activation, stochastic=stochastic, seed=seed)
+        policy.out = act
         return policy
 
     # ---- policy in the loop, replayed as one CUDA graph ------------------------------------------------
@@ -546,7 +551,28 @@ class GraphedRollout:
         step = env.core.bind_step(env._state, env._obs, env._reward, env._term.view(torch.uint8), env._rem,
                                   env._atb.view(torch.uint8), variant=env._variant(), action_dtype=torch.uint8)
 
+        fused = getattr(policy, "fuse_step", False) and hasattr(policy, "mlp")
+        if fused:
+            act2 = torch.zeros(n, dtype=torch.uint8, device=dev)  # the policy's output alternates between two buffers
+
+        def body_fused():
+            # iteration k is ONE launch: the step of action k and the policy's action k + 1 from the fresh observations
+            # (`w2a_step_mlp`); the observation tensor is written for whoever trains on it, never read back here
+            self.returns.zero_()
+            cur, nxt = policy(env._obs), act2
+            for _ in range(steps):
+                env.core.step_mlp(env._state, cur, env._obs, env._reward, env._term.view(torch.uint8), env._rem,
+                                  env._atb.view(torch.uint8), next_action=nxt, logit=policy.logits, ep_return=self.returns,
+                                  step=policy.calls, variant=env._variant(), **policy.mlp)
+                policy.calls += 1
+                if env.stats is not None:
+                    env.stats.update(cur, env._reward, env._term, env._atb)
+                cur, nxt = nxt, cur
+            self._reset_tail()
+
         def body():
+            if fused:
+                return body_fused()
             self.returns.zero_()
             for _ in range(steps):
                 a = policy(env._obs)
@@ -559,15 +585,7 @@ class GraphedRollout:
                 if env.stats is not None:
                     env.stats.update(act, env._reward, env._term, env._atb)
                 self.returns.add_(env._reward)
-            if reset_at_end:
-                s = env._draw()
-                env._idx = s
-                env.core.reset(env._state, env._obs, s["loc"], s["year"], s["coef_col"], s["coef_idx"],
-                               budget=s.get("budget"), remaining=env._rem)
-                for dst, key in ((env._ep_loc, "loc"), (env._ep_year, "year"), (env._coef_col, "coef_col"),
-                                 (env._list_idx, "list_idx")):
-                    dst.copy_(s[key])
-                env._atb.zero_()
+            self._reset_tail()
 
         # warm up on a side stream (lazy initialisation of torch kernels and of the launch tables), on
         # a copy of the env state so that the capture starts from where the env is now
@@ -594,6 +612,20 @@ class GraphedRollout:
         with torch.cuda.graph(self.graph):
             body()
         # the capture itself does not execute anything: the env is still where it was
+
+    def _reset_tail(self):
+        """the captured reset of all envs that ends a summer (`reset_at_end`)"""
+        env = self.env
+        if not self.reset_at_end:
+            return
+        s = env._draw()
+        env._idx = s
+        env.core.reset(env._state, env._obs, s["loc"], s["year"], s["coef_col"], s["coef_idx"],
+                       budget=s.get("budget"), remaining=env._rem)
+        for dst, key in ((env._ep_loc, "loc"), (env._ep_year, "year"), (env._coef_col, "coef_col"),
+                         (env._list_idx, "list_idx")):
+            dst.copy_(s[key])
+        env._atb.zero_()
 
     def replay(self) -> torch.Tensor:
         env = self.env
