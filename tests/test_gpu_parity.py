@@ -425,6 +425,16 @@ def test_real_shape_million_envs_vs_c_oracle(real_shape):
     assert max(worst.values()) < 1e-5
 
 
+@pytest.mark.parametrize("n", [4096, 75_776, 75_809])
+def test_real_shape_small_sets_both_table_instances(real_shape, n):
+    """BASELINE configs[1] (4 096 envs) and the two sides of the switch between the latency-tuned instance of the TABLE
+    step (one warp per CTA, every gather of a group in flight; up to 16 groups per SM = 75 776 envs on 148 SMs) and the
+    bandwidth instance, on the real-shape tables against the C oracle."""
+    store, weights, core = real_shape["linear"]
+    worst = _against_c_oracle(store, weights, core, n, 10, ("table", "coop"), seed=n)
+    assert max(worst.values()) < 1e-5
+
+
 def test_real_shape_ragged_days_on_the_table_path(real_shape):
     """Envs on different days of the summer (masked reset mid-way) keep using the tabulated logits: every env looks
     its own day up in the whole-summer tables; checked against the C oracle on the real shape."""
