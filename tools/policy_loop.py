@@ -13,10 +13,12 @@ store, weights = bench.make_tables()
 n = 1 << 20
 venv = HeatAlertVectorEnv(n, weights=weights, store=store, seed=5, device="cuda:0", sort_episodes="--sorted" in sys.argv)
 venv.reset()
-g = torch.Generator(device="cuda").manual_seed(1)
-w1 = torch.randn(64, 29, generator=g, device="cuda") * 0.3
-w2 = torch.randn(64, generator=g, device="cuda")
-pol = venv.mlp_policy(w1, torch.zeros(64, device="cuda"), w2, 0.0)
+g = torch.Generator(device="cuda").manual_seed(int(next((a[6:] for a in sys.argv if a.startswith("--seed")), 1)))
+B2 = float(next((a[4:] for a in sys.argv if a.startswith("--b2")), 0.0))
+H = int(next((a[2:] for a in sys.argv if a.startswith("-H")), 64))
+w1 = torch.randn(H, 29, generator=g, device="cuda") * 0.3
+w2 = torch.randn(H, generator=g, device="cuda")
+pol = venv.mlp_policy(w1, torch.zeros(H, device="cuda"), w2, B2)
 pol.fuse_step = "--two-launches" not in sys.argv
 if "--fused-eager" in sys.argv:  # the one-launch form without a graph, for `ncu -k regex:step_mlp_kernel`
     cur, nxt = pol(venv._obs), torch.zeros(n, dtype=torch.uint8, device="cuda")
@@ -45,4 +47,4 @@ else:
         roll.replay()
     e1.record()
     torch.cuda.synchronize()
-    print(json.dumps({"us_per_step": e0.elapsed_time(e1) / 3 / roll.steps * 1e3}))
+    print(json.dumps({"us_per_step": round(e0.elapsed_time(e1) / 3 / roll.steps * 1e3, 2), "alert_rate_last_step": round(float(pol.out.float().mean()), 3), "mean_return": round(float(roll.returns.mean()), 1)}))

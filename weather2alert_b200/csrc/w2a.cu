@@ -76,6 +76,8 @@ struct w2a_ctx {
   std::vector<int32_t> col_to_loc_host;  // host copy of the county map (canonical check of the *_host resets)
   int64_t keep_state_max_envs = 3 << 19;  // W2A_KEEP_STATE_MAX overrides (0 = never)
   int small_table_groups_per_sm = 16;  // TABLE step: env sets of up to this many 32-env groups per SM take the one-warp-per-CTA instance (W2A_SMALL_TABLE overrides, 0 = never)
+  bool pdl_policy = false;        // the policy and step + policy kernels are launched serialised: as programmatic dependents they run
+                                  // 1-10 us per iteration SLOWER in the graphed loop (B200, 2^20 envs; W2A_PDL_POLICY=1 to compare)
   bool pdl = true;                // step kernels are launched with programmatic stream serialization (W2A_PDL=0: off)
   const void* occ_key[kMaxKernels] = {};  // occupancy (CTAs per SM) of each kernel launched so far
   int occ_val[kMaxKernels] = {};
@@ -288,6 +290,7 @@ int w2a_create(int device, w2a_ctx** out) {
   ctx->pdl = !(pdl_env && pdl_env[0] == '0');
   if (const char* ks = std::getenv("W2A_KEEP_STATE_MAX")) ctx->keep_state_max_envs = std::atoll(ks);
   if (const char* sm = std::getenv("W2A_SMALL_TABLE")) ctx->small_table_groups_per_sm = std::atoi(sm);
+  if (const char* pp = std::getenv("W2A_PDL_POLICY")) ctx->pdl_policy = std::atoi(pp) != 0;
   if (const char* hc = std::getenv("W2A_HOST_CHUNK")) g_host_chunk = std::max<int64_t>(1024, std::atoll(hc));
   *out = ctx;
   return W2A_OK;
@@ -828,7 +831,7 @@ int launch_policy(w2a_ctx* ctx, cudaStream_t st, const w2a::PolicyMlpArgs& a) {
     int grid = 0;
     int rc2 = grid_for(ctx, kernel, kBlock, smem, kBlock, a.n, &grid);
     if (rc2) return rc2;
-    W2A_CUDA(ctx, launch_kernel(kernel, grid, kBlock, smem, st, ctx->pdl, a));
+    W2A_CUDA(ctx, launch_kernel(kernel, grid, kBlock, smem, st, ctx->pdl && ctx->pdl_policy, a));
     return W2A_OK;
   });
   if (rc) return rc;
@@ -897,7 +900,7 @@ int w2a_step_mlp(w2a_ctx* ctx, void* stream, int64_t n, const uint8_t* action, v
     int grid = 0;
     int rc2 = grid_for(ctx, kernel, kBlock, w2a::kStepMlpSmemBytes, kBlock, n, &grid);
     if (rc2) return rc2;
-    W2A_CUDA(ctx, launch_kernel(kernel, grid, kBlock, w2a::kStepMlpSmemBytes, st, ctx->pdl, a, m, ep_return));
+    W2A_CUDA(ctx, launch_kernel(kernel, grid, kBlock, w2a::kStepMlpSmemBytes, st, ctx->pdl && ctx->pdl_policy, a, m, ep_return));
     return W2A_OK;
   });
   if (rc) return rc;

@@ -253,11 +253,15 @@ __global__ void __launch_bounds__(32 * kPolWarps, 5) policy_mlp_kernel(const Pol
 // step's warp evaluates the policy on its 32 fresh rows while they sit in its staging buffer, on their way out: the
 // launch takes the actions of step k, writes observation, reward and flags of step k as the plain step does, AND the
 // policy's actions for step k + 1 -- the tensor-core work fills issue slots the memory-bound step leaves idle.
+#ifndef W2A_STEP_MLP_PREFETCH
+#define W2A_STEP_MLP_PREFETCH 1  // L2 prefetch of the next group's sector and rows before the policy of this one
+#endif
 #ifndef W2A_STEP_MLP_MT
 #define W2A_STEP_MLP_MT 1  // m-tiles of the policy per pass inside the step kernel (1: half the registers, occupancy matters more)
 #endif
 template <int NT, int ACT>
 struct StepMlpPost {
+  static constexpr bool kPrefetchNext = W2A_STEP_MLP_PREFETCH != 0;
   const PolicyMlpArgs& m;
   double* ep_return;  // optional: += reward per env (the return of the rollout so far)
   unsigned* w1s;
