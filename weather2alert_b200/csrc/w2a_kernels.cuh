@@ -762,7 +762,6 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 // `post` hooks a consumer of the fresh observations into the kernel (w2a_policy.cuh: the MLP policy that picks the next
 // action from the rows while they are still in shared memory); StepNoPost is the plain step.
 struct StepNoPost {
-  static constexpr bool kPrefetchNext = false;
   __device__ __forceinline__ void reward(int, float) const {}
   __device__ __forceinline__ void group(const float*, int, int) const {}
 };
@@ -956,15 +955,6 @@ __device__ __forceinline__ void step_table_body(const StepArgs& p, Post& post) {
         const int env = (i * 565) >> 14;  // i / 29 for i < 928
         if ((wmask >> env) & 1u) st_stream(ob + i, stage[i]);
       }
-    }
-    if (Post::kPrefetchNext && wg + warps_total < n_groups) {
-      // the consumer below keeps this warp busy for a while: ask L2 for the next group's sector and row lines now (its
-      // state has arrived by this point; the row is the one a plain mid-summer step will want -- a hint, nothing more)
-      const unsigned t_n = mv_n.y & 0xffu, days_n = sv_n.x >> 24;
-      const unsigned row_n = (sv_n.x & 0xffffffu) + min(t_n + 1u, days_n - 1u);
-      const unsigned entry_n = (mv_n.y >> 31) ? (t_n * p.tb.n_records + (sv_n.y & kRecMask)) * static_cast<unsigned>(p.tb.Y) + (sv_n.y >> 24) : 0u;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.tb.z32_all + static_cast<size_t>(entry_n) * 2));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.tb.x32 + static_cast<size_t>(row_n) * 32));
     }
     post.group(stage, base, min(32, p.n - base));  // the group's 32 rows as the observation tensor holds them
     __syncwarp();

@@ -119,6 +119,7 @@ __device__ __forceinline__ void mlp_group(const PolicyMlpArgs& p, const float* r
                                           const unsigned (&w2f)[NT / 2][2], int base, int n_valid) {
   const int lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
+  const unsigned w1_lane = static_cast<unsigned>(__cvta_generic_to_shared(w1s + (lane & 7) * kPolWStride + (lane >> 3) * 4));
 #pragma unroll
   for (int m0 = 0; m0 < 2; m0 += MT) {
     // ---- A fragments: [MT m-tiles of 16 envs] x [2 k-steps of 16 slots] ------------------------------------------
@@ -156,14 +157,19 @@ __device__ __forceinline__ void mlp_group(const PolicyMlpArgs& p, const float* r
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[jj][m][c] = 0.f;
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj)
+      for (int jj = 0; jj < 2; ++jj) {
+        // the four B fragments of n-tile 2u + jj (8 hidden units x 32 slots) in one instruction: lane i hands in the
+        // address of row i % 8, 16-byte column i / 8 of the tile (80-byte row stride: conflict-free)
+        unsigned b[4];
+        const unsigned waddr = w1_lane + static_cast<unsigned>((8 * (2 * u + jj)) * kPolWStride * sizeof(unsigned));
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
+                     : "r"(waddr));
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const unsigned* wrow = w1s + (8 * (2 * u + jj) + gid) * kPolWStride + 8 * ks + tig;
-          const unsigned b0 = wrow[0], b1 = wrow[4];
+        for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-          for (int m = 0; m < MT; ++m) mma_f16(acc[jj][m], a[m][ks], b0, b1);
-        }
+          for (int m = 0; m < MT; ++m) mma_f16(acc[jj][m], a[m][ks], b[2 * ks], b[2 * ks + 1]);
+      }
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         unsigned hfrag[4];  // C layout of n-tiles (2u, 2u + 1) = A layout of the 16 x 16 tile of hidden units 16u .. 16u + 15
@@ -253,15 +259,11 @@ __global__ void __launch_bounds__(32 * kPolWarps, 5) policy_mlp_kernel(const Pol
 // step's warp evaluates the policy on its 32 fresh rows while they sit in its staging buffer, on their way out: the
 // launch takes the actions of step k, writes observation, reward and flags of step k as the plain step does, AND the
 // policy's actions for step k + 1 -- the tensor-core work fills issue slots the memory-bound step leaves idle.
-#ifndef W2A_STEP_MLP_PREFETCH
-#define W2A_STEP_MLP_PREFETCH 1  // L2 prefetch of the next group's sector and rows before the policy of this one
-#endif
 #ifndef W2A_STEP_MLP_MT
 #define W2A_STEP_MLP_MT 1  // m-tiles of the policy per pass inside the step kernel (1: half the registers, occupancy matters more)
 #endif
 template <int NT, int ACT>
 struct StepMlpPost {
-  static constexpr bool kPrefetchNext = W2A_STEP_MLP_PREFETCH != 0;
   const PolicyMlpArgs& m;
   double* ep_return;  // optional: += reward per env (the return of the rollout so far)
   unsigned* w1s;
