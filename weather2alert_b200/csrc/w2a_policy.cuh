@@ -1,4 +1,5 @@
-// w2a_policy.cuh -- a small MLP policy on the 29-slot observation, evaluated on the device between two steps.
+// w2a_policy.cuh -- a small MLP policy on the 29-slot observation, evaluated on the device between two steps
+// (policy_mlp_kernel) or inside the step launch itself (step_mlp_kernel, at the end of this file).
 //
 // the reference's driver loop is `a = policy(obs); env.step(a)` (env.py:273-276 with a policy in
 // place of `action_space.sample()`).  With the step kernel at ~35 us per 2^20 envs, a policy built from framework
@@ -24,7 +25,7 @@
 namespace w2a {
 
 constexpr int kPolMaxHidden = 64;
-constexpr int kPolK = 32;        // 29 observation slots padded to 4 k-steps of 8
+constexpr int kPolK = 32;        // 29 observation slots + the constant-1 input of the bias (k = 29), padded to 2 k-steps of 16
 constexpr int kPolWStride = 20;  // shared-memory row stride of W1 in half2 words (16 + 4): conflict-free B-fragment reads
 
 struct PolicyMlpArgs {
