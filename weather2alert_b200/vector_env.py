@@ -260,9 +260,22 @@ class HeatAlertVectorEnv(VectorEnv):
                 raise KeyError((sp.fips_list[int(list_idx[b])], int(year[b])))
         list_idx = info_idx
         if self.sort_episodes and sort:
-            key = ((loc * self.core.Sw + coef_col) * sp.n_samples + coef_idx) * self.core.Y + year
-            order = torch.argsort(key)
-            loc, year, coef_col, coef_idx, list_idx = (v[order] for v in (loc, year, coef_col, coef_idx, list_idx))
+            Sw, P, Y = self.core.Sw, sp.n_samples, self.core.Y
+            key = ((loc * Sw + coef_col) * P + coef_idx) * Y + year
+            if list_idx is coef_col:
+                # no augmentation: the key holds everything -- sort the keys alone (32-bit when they fit: half the radix
+                # passes) and take the streams apart again, instead of an argsort and five gathers
+                if self.core.S * Sw * P * Y < 2**31:
+                    key = key.int()
+                key = torch.sort(key).values.long()
+                year = key % Y
+                coef_idx = (key // Y) % P
+                coef_col = (key // (Y * P)) % Sw
+                loc = key // (Y * P * Sw)
+                list_idx = coef_col
+            else:
+                order = torch.argsort(key)
+                loc, year, coef_col, coef_idx, list_idx = (v[order] for v in (loc, year, coef_col, coef_idx, list_idx))
         s = dict(loc=loc.int(), year=year.int(), coef_col=coef_col.int(), coef_idx=coef_idx.int(),
                  list_idx=list_idx.int())
         budget = o.get("budget", self.budget)
