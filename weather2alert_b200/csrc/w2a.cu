@@ -237,9 +237,16 @@ int reset_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const int32_t* loc, c
   a.remaining = remaining;
   a.n = static_cast<int>(n);
   int grid = 0;
-  int rc = grid_for(ctx, w2a::reset_kernel, 256, 0, 256, n, &grid);
-  if (rc) return rc;
-  w2a::reset_kernel<<<grid, 256, 0, st>>>(a);
+  if (ctx->tb.x32) {  // the float32 observation rows exist: one 128-byte gather per env, bulk stores
+    constexpr int kBlock = 32 * w2a::kTableWarps;
+    int rc = grid_for(ctx, w2a::reset_table_kernel, kBlock, w2a::kTableSmemBytes, kBlock, n, &grid);
+    if (rc) return rc;
+    w2a::reset_table_kernel<<<grid, kBlock, w2a::kTableSmemBytes, st>>>(a);
+  } else {
+    int rc = grid_for(ctx, w2a::reset_kernel, 256, 0, 256, n, &grid);
+    if (rc) return rc;
+    w2a::reset_kernel<<<grid, 256, 0, st>>>(a);
+  }
   ctx->launches++;
   W2A_CUDA(ctx, cudaGetLastError());
   return W2A_OK;

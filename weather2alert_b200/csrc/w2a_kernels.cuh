@@ -1030,6 +1030,78 @@ __global__ void __launch_bounds__(256) reset_kernel(const ResetArgs p) {
   }
 }
 
+// The same reset once the float32 observation rows exist (w2a_precompute_logits): the first observation is the row of
+// day 0 as it lies in x32 plus the remaining budget -- one 128-byte gather per env (8 lanes per row) instead of a
+// 256-byte float64 record and 29 scalar stores, staged and written with one bulk store per full group like the TABLE step.
+__global__ void __launch_bounds__(32 * kTableWarps, 8) reset_table_kernel(const ResetArgs p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* const stage = reinterpret_cast<TableScratchWarp*>(smem_raw)[threadIdx.x >> 5].obs;
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 7;
+  const int g = lane >> 3;
+  const float4* const x32_lane = reinterpret_cast<const float4*>(p.tb.x32) + q;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int n_groups = (p.n + 31) >> 5;
+  const unsigned long long stream_out = l2_policy_evict_first();
+  const bool obs_aligned = (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
+  bool bulk_pending = false;
+  for (int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wg < n_groups; wg += warps_total) {
+    const int base = wg << 5;
+    const int e = base + lane;
+    const bool valid = e < p.n;
+    const int ec = valid ? e : p.n - 1;
+    const bool take = valid && (p.mask == nullptr || p.mask[ec] != 0);
+    const int locv = __ldcs(p.loc + ec), yearv = __ldcs(p.year + ec), colv = __ldcs(p.coef_col + ec);
+    const int sy = locv * p.tb.Y + yearv;
+    const unsigned nd = __ldg(p.tb.n_days + sy);
+    const unsigned row0 = static_cast<unsigned>(sy) * static_cast<unsigned>(p.tb.T);
+    int budget = p.budget ? __ldcs(p.budget + ec) : INT32_MIN;
+    if (budget == INT32_MIN) budget = __ldg(p.tb.budget0 + sy);  // env.py:167-170
+    const unsigned cv = static_cast<unsigned>(colv) * static_cast<unsigned>(p.tb.P) + static_cast<unsigned>(__ldcs(p.coef_idx + ec));
+    const bool canon = p.tb.col_to_loc != nullptr && __ldg(p.tb.col_to_loc + colv) == locv;
+    float4 rows[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) rows[it] = __ldg(x32_lane + static_cast<size_t>(__shfl_sync(kFull, row0, 4 * it + g)) * 8);
+    if (take) {
+      st_stream(p.st_static + e, make_uint2(row0 | (nd << 24), cv | (static_cast<unsigned>(yearv) << 24)));
+      st_stream(p.st_mut + e, make_uint2(static_cast<unsigned>(budget), canon ? 0x80000000u : 0u));  // t = streak = win = 0
+      if (p.remaining) p.remaining[e] = budget;
+    }
+    const unsigned wmask = __ballot_sync(kFull, take);
+    if (bulk_pending) {  // the previous group's bulk store must have finished reading the staging buffer
+      if (lane == 0) bulk_store_wait_read();
+      __syncwarp();
+      bulk_pending = false;
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      float* st = stage + (4 * it + g) * kObsDim + 4 * q;
+      st[0] = rows[it].x;
+      if (q < 7) {
+        st[1] = rows[it].y;
+        st[2] = rows[it].z;
+        st[3] = rows[it].w;
+      }
+    }
+    __syncwarp();
+    stage[lane * kObsDim + 25] = static_cast<float>(budget);  // remaining_budget = budget; lag, streak, alerts_2wks are 0 in x32
+    fence_proxy_async_smem();
+    __syncwarp();
+    float* const ob = p.obs + static_cast<size_t>(base) * kObsDim;
+    if (wmask == kFull && obs_aligned) {
+      if (lane == 0) bulk_store(ob, stage, kObsBlockBytes, stream_out);
+      bulk_pending = true;
+    } else if (wmask != 0u) {  // masked reset or ragged tail: the other envs keep their observation
+      for (int i = lane; i < 32 * kObsDim; i += 32) {
+        const int env = (i * 565) >> 14;  // i / 29 for i < 928
+        if ((wmask >> env) & 1u) st_stream(ob + i, stage[i]);
+      }
+    }
+    __syncwarp();
+  }
+  if (bulk_pending && lane == 0) bulk_store_wait_all();
+}
+
 // =========================================================================================
 // rollout: the whole `while not done: step(a)` loop (env.py:273-276) of every env in one
 // launch.  Observations are not materialised; what comes out is the sum of rewards per env,
