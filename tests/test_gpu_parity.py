@@ -265,6 +265,9 @@ def test_abi_error_paths():
     assert b"w2a_set_features" in lib.w2a_last_error(ctx)
     assert lib.w2a_step_host(ctx, None, None, None, None, None, None) == -3
     assert lib.w2a_set_coefs(ctx, None, 1, 1) == -1
+    nul = [None] * 6
+    assert lib.w2a_step_mlp(ctx, None, 8, None, *nul, 3, None, None, None, 0.0, 8, 0, 0, 0, 0, None, None, None) == -3  # tables missing
+    assert lib.w2a_policy_mlp(ctx, None, 8, None, None, None, None, 0.0, 8, 0, 0, 0, 0, None, None) == -1  # NULL arguments
     assert lib.w2a_destroy(ctx) == 0
 
 

@@ -871,6 +871,7 @@ int w2a_step_mlp(w2a_ctx* ctx, void* stream, int64_t n, const uint8_t* action, v
   if (rc) return rc;
   if (n == 0) return W2A_OK;
   if (!action || !state || !obs || !reward || !terminated) return fail(ctx, W2A_E_INVALID, "w2a_step_mlp: NULL argument");
+  if (next_action == action) return fail(ctx, W2A_E_INVALID, "w2a_step_mlp: next_action must not alias action (alternate two buffers)");
   w2a::PolicyMlpArgs m;
   rc = fill_policy_args(ctx, "w2a_step_mlp", n, obs, w1, b1, w2, b2, hidden, activation, stochastic, seed, step, next_action,
                         logit, &m);
