@@ -154,3 +154,52 @@ def test_step_mlp_is_step_then_policy(golden, H, activation, stochastic):
     with pytest.raises(ValueError, match="alias"):
         core.step_mlp(one["state"], one["a"][0], one["obs"], one["reward"], one["term"], one["rem"], one["atb"], w1, b1, w2, 0.0,
                       one["a"][0])
+
+
+def test_step_mlp_at_the_benchmarked_shape():
+    """2^20 envs on the bench's own tables (746 x 11 x 153 x 100): five iterations of the one-launch form against
+    step + policy as two launches -- every output byte identical -- and the step's part against the C oracle."""
+    import bench
+    from oracle import c_oracle
+    from weather2alert_b200 import _lib
+    from weather2alert_b200.core import HeatAlertCore
+
+    store, weights = bench.make_tables()
+    core = HeatAlertCore(store, weights, "cuda:0")
+    n, H = 1 << 20, 64
+    s = bench.index_streams(store, weights, n, 0, False, "interleaved")
+    idx = {k: torch.from_numpy(v).cuda() for k, v in s.items()}
+    g = torch.Generator(device="cuda").manual_seed(3)
+    w1 = torch.randn(H, 29, generator=g, device="cuda") * 0.3
+    w1[:, 17] *= 0.02
+    b1, w2 = torch.randn(H, generator=g, device="cuda") * 0.1, torch.randn(H, generator=g, device="cuda") * 0.5
+
+    def buffers():
+        st, ob = core.alloc_state(n), torch.zeros((n, 29), device="cuda")
+        core.reset(st, ob, idx["loc"], idx["year"], idx["coef_col"], idx["coef_idx"])
+        return dict(state=st, obs=ob, reward=torch.zeros(n, device="cuda"), term=torch.zeros(n, dtype=torch.uint8, device="cuda"),
+                    rem=torch.zeros(n, dtype=torch.int32, device="cuda"), atb=torch.zeros(n, dtype=torch.uint8, device="cuda"),
+                    a=[torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(2)], logit=torch.zeros(n, device="cuda"),
+                    ret=torch.zeros(n, dtype=torch.float64, device="cuda"))
+
+    one, two = buffers(), buffers()
+    co = c_oracle.COracle(store.feat, store.sig_code, store.n_days, weights.coef, n)
+    co.reset(s["loc"], s["year"], s["coef_col"], s["coef_idx"])
+    for b in (one, two):
+        core.policy_mlp(b["obs"], w1, b1, w2, 0.3, b["a"][0], logit=b["logit"])
+    for k in range(5):
+        cur, nxt = k & 1, (k + 1) & 1
+        act = one["a"][cur].cpu().numpy()
+        core.step_mlp(one["state"], one["a"][cur], one["obs"], one["reward"], one["term"], one["rem"], one["atb"], w1, b1, w2, 0.3,
+                      one["a"][nxt], logit=one["logit"], ep_return=one["ret"], variant=_lib.STEP_TABLE)
+        core.step(two["state"], two["a"][cur], two["obs"], two["reward"], two["term"], two["rem"], two["atb"], variant=_lib.STEP_TABLE)
+        two["ret"] += two["reward"]
+        core.policy_mlp(two["obs"], w1, b1, w2, 0.3, two["a"][nxt], logit=two["logit"])
+        for key in ("state", "obs", "reward", "term", "rem", "atb", "logit", "ret"):
+            assert torch.equal(one[key].view(torch.uint8), two[key].view(torch.uint8)), (k, key)
+        assert torch.equal(one["a"][nxt], two["a"][nxt]), k
+        o_ref, r_ref, d_ref, rem_ref, atb_ref = co.step(act)
+        np.testing.assert_array_equal(one["obs"].cpu().numpy(), o_ref.astype(np.float32))
+        np.testing.assert_allclose(one["reward"].cpu().numpy(), r_ref, rtol=1e-5, atol=1e-10)
+        np.testing.assert_array_equal(one["rem"].cpu().numpy(), rem_ref)
+    assert 0.01 < float(one["a"][0].float().mean()) < 0.99
