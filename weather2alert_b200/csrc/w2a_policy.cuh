@@ -260,6 +260,9 @@ __global__ void __launch_bounds__(32 * kPolWarps, 5) policy_mlp_kernel(const Pol
 // step's warp evaluates the policy on its 32 fresh rows while they sit in its staging buffer, on their way out: the
 // launch takes the actions of step k, writes observation, reward and flags of step k as the plain step does, AND the
 // policy's actions for step k + 1 -- the tensor-core work fills issue slots the memory-bound step leaves idle.
+#ifndef W2A_STEP_MLP_ROWS
+#define W2A_STEP_MLP_ROWS 1  // rounds of row gathers in flight in the fused kernel (B200, 7 CTAs/SM: 1 / 2 / 4 rounds = 52.6 / 53.1 / 56.3 us)
+#endif
 #ifndef W2A_STEP_MLP_MT
 #define W2A_STEP_MLP_MT 1  // m-tiles of the policy per pass inside the step kernel (1: half the registers, occupancy matters more)
 #endif
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_STEP_MLP_MINBLOCKS) step
   pdl_wait();
   mlp_load_weights<NT>(m, post.w1s, post.w2f);
   __syncthreads();
-  step_table_body<ADT, W2A_TABLE_ROWS>(p, post);
+  step_table_body<ADT, W2A_STEP_MLP_ROWS>(p, post);
 }
 
 }  // namespace w2a
