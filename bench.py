@@ -405,7 +405,9 @@ def run_ours(args):
     actions = (torch.rand((T, n), generator=g, device=dev) < 0.5).to(torch.uint8)
 
     # ---- device-resident throughput: `value` ---------------------------------------------------
-    es = EnvSet(core, idx, n, T, actions, variant, use_graph=not args.no_graph)
+    # env slots in table order: tell the step (the hint HeatAlertVectorEnv passes for its locality-sorted resets)
+    local_hint = _lib.STEP_LOCAL if (args.locality == "sorted" and variant == _lib.STEP_TABLE) else 0
+    es = EnvSet(core, idx, n, T, actions, variant | local_hint, use_graph=not args.no_graph)
     es.reset()
     es.run(3)  # warm every lazy path (occupancy queries, attributes) before any capture
     torch.cuda.synchronize()
@@ -424,8 +426,8 @@ def run_ours(args):
     sorted_info = None
     if args.locality == "interleaved" and not args.no_extras:
         s2 = index_streams(store, weights, n, rank, wl["augment"], "sorted")
-        es2 = EnvSet(core, {k: torch.from_numpy(v).to(dev) for k, v in s2.items()}, n, T, actions, variant,
-                     use_graph=not args.no_graph)
+        es2 = EnvSet(core, {k: torch.from_numpy(v).to(dev) for k, v in s2.items()}, n, T, actions,
+                     variant | (_lib.STEP_LOCAL if variant == _lib.STEP_TABLE else 0), use_graph=not args.no_graph)
         t2, _, _, _ = timed_steps(es2, K, W, world, dist)
         ms2 = all_max(statistics.median(t2))
         sorted_info = {"value": n * world * K / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K,
@@ -455,7 +457,7 @@ def run_ours(args):
         vms = all_max(v0.elapsed_time(v1)) / T
         venv_info = {"value": n * world / (vms * 1e-3), "unit": UNIT, "ms_per_step": vms,
                      "roofline_frac": BYTES_STREAMING * n / (vms * 1e-3) / 1e9 / load_peaks()[0],
-                     "kernel": kernel_names[venv._variant()], "sort_episodes": venv.sort_episodes,
+                     "kernel": kernel_names[venv._variant() & 0xff], "sort_episodes": venv.sort_episodes,
                      "note": "HeatAlertVectorEnv(num_envs, core=...) with default arguments: .step(actions) called from "
                              "Python 153 times (no CUDA graph), the autoreset of all envs included"}
         del venv

@@ -45,6 +45,11 @@ extern "C" {
 #define W2A_X_STRIDE 32 /* float64 per day-row: 0..23 table reward features, 24 significance code, 25 gate, 26..31 zero */
 #define W2A_W_STRIDE 64 /* float32 per (county, posterior sample): (baseline, effectiveness) pairs */
 
+/* OR into `variant`: the env slots are in table order (e.g. sorted by county, sample, year), so that neighbouring envs
+ * share table lines -- W2A_STEP_TABLE then keeps two rounds of row gathers in flight at every size (a tuning hint:
+ * results never depend on it) */
+#define W2A_STEP_LOCAL 0x100
+
 /* action_dtype */
 #define W2A_ACT_U8 0
 #define W2A_ACT_I32 1

@@ -438,6 +438,32 @@ def test_real_shape_small_sets_both_table_instances(real_shape, n):
     assert max(worst.values()) < 1e-5
 
 
+def test_table_instances_and_the_locality_hint_never_change_a_result(real_shape):
+    """`W2A_STEP_TABLE` has three instances (one / two / eight row rounds in flight, picked by env-set size and by the
+    `W2A_STEP_LOCAL` hint): same bytes out of each, on interleaved and on sorted slots."""
+    import bench
+    from weather2alert_b200 import _lib
+
+    store, weights, core = real_shape["linear"]
+    n = 200_000  # above the small-set switch, below the one-round limit: the hint switches one <-> two rounds
+    for locality in ("interleaved", "sorted"):
+        s = bench.index_streams(store, weights, n, 0, False, locality)
+        idx = {k: torch.from_numpy(v).cuda() for k, v in s.items()}
+        out = []
+        for variant in (_lib.STEP_TABLE, _lib.STEP_TABLE | _lib.STEP_LOCAL):
+            st, ob = core.alloc_state(n), torch.zeros((n, 29), device="cuda")
+            core.reset(st, ob, idx["loc"], idx["year"], idx["coef_col"], idx["coef_idx"])
+            rew, term = torch.zeros(n, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+            rem, atb = torch.zeros(n, dtype=torch.int32, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+            g = torch.Generator(device="cuda").manual_seed(5)
+            for _ in range(6):
+                a = (torch.rand(n, generator=g, device="cuda") < 0.4).to(torch.uint8)
+                core.step(st, a, ob, rew, term, rem, atb, variant=variant)
+            out.append((st.clone(), ob.clone(), rew.clone(), term.clone(), rem.clone(), atb.clone()))
+        for x, y in zip(*out):
+            assert torch.equal(x.view(torch.uint8), y.view(torch.uint8)), locality
+
+
 def test_real_shape_ragged_days_on_the_table_path(real_shape):
     """Envs on different days of the summer (masked reset mid-way) keep using the tabulated logits: every env looks
     its own day up in the whole-summer tables; checked against the C oracle on the real shape."""

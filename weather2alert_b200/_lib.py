@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("W2A_LIB_PATH") or os.path.join(_HERE, "libw2a.so")
 W2A_OK = 0
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 STEP_AUTO, STEP_THREAD, STEP_COOP, STEP_TABLE = 0, 1, 2, 3
+STEP_LOCAL = 0x100  # OR into a variant: env slots are in table order (tuning hint, w2a.h)
 POLICY_LEN = 30  # W2A_POLICY_LEN: one weight per observation slot + bias
 BUDGET_DEFAULT = -(2**31)
 OBS_DIM = 29

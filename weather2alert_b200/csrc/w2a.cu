@@ -45,6 +45,7 @@ struct HostEnvs {
   // resets): when all do and the whole-summer tables exist, the step runs the TABLE variant
   std::vector<uint8_t> noncanon;
   int64_t n_noncanon = 0;
+  bool local = false;  // the last full reset's index streams were in (county, column, sample, year) order: W2A_STEP_LOCAL
   bool ever_reset = false;
   cudaStream_t streams[kHostStreams] = {};
   cudaEvent_t kernels_done[kHostStreams] = {};  // last step kernel of each stream: the small outputs leave after all of them
@@ -60,7 +61,7 @@ struct HostEnvs {
 constexpr int64_t kHostPackedMax = 1024;
 
 char g_create_error[512] = "";
-constexpr int kMaxKernels = 32;
+constexpr int kMaxKernels = 48;
 
 }  // namespace
 
@@ -75,6 +76,7 @@ struct w2a_ctx {
   void* table_scratch = nullptr;  // z32_all | zt_all | x32 | pt, owned by the context (w2a_precompute_logits)
   std::vector<int32_t> col_to_loc_host;  // host copy of the county map (canonical check of the *_host resets)
   int64_t keep_state_max_envs = 3 << 19;  // W2A_KEEP_STATE_MAX overrides (0 = never)
+  int64_t table_rows1_max_envs = 3 << 20;  // TABLE step without the locality hint: up to this many envs one row round in flight (W2A_TABLE_ROWS1_MAX)
   int small_table_groups_per_sm = 16;  // TABLE step: env sets of up to this many 32-env groups per SM take the one-warp-per-CTA instance (W2A_SMALL_TABLE overrides, 0 = never)
   bool pdl_policy = false;        // the policy and step + policy kernels are launched serialised: as programmatic dependents they run
                                   // 1-10 us per iteration SLOWER in the graphed loop (B200, 2^20 envs; W2A_PDL_POLICY=1 to compare)
@@ -147,20 +149,24 @@ int grid_for(w2a_ctx* ctx, K kernel, int block, size_t smem, int64_t work_items_
 }
 
 template <int ADT>
-int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int variant) {
+int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int variant, bool local) {
   int grid = 0;
   if (variant == W2A_STEP_TABLE) {
     constexpr int kBlock = 32 * w2a::kTableWarps;
-    int rc = grid_for(ctx, w2a::step_table_kernel<ADT>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);
-    if (rc) return rc;
     // small env sets (a step is a chain of memory latencies, not bandwidth): one warp per CTA so that the groups spread
     // over the SMs, and all eight row gathers of a group in flight together
     const int64_t groups = (static_cast<int64_t>(a.n) + 31) / 32;
     if (groups <= static_cast<int64_t>(ctx->small_table_groups_per_sm) * ctx->sm_count) {
       W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT, 8>, static_cast<int>(groups), 32,
                                   sizeof(w2a::TableScratchWarp), st, ctx->pdl, a));
+    } else if (!local && a.n <= ctx->table_rows1_max_envs) {  // no locality, not yet bandwidth-bound: one row round in flight
+      int rc = grid_for(ctx, w2a::step_table_kernel<ADT, 1>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);
+      if (rc) return rc;
+      W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT, 1>, grid, kBlock, w2a::kTableSmemBytes, st, ctx->pdl, a));
     } else {
-      W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT>, grid, kBlock, w2a::kTableSmemBytes, st, ctx->pdl, a));
+      int rc = grid_for(ctx, w2a::step_table_kernel<ADT, 2>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);
+      if (rc) return rc;
+      W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT, 2>, grid, kBlock, w2a::kTableSmemBytes, st, ctx->pdl, a));
     }
   } else if (variant == W2A_STEP_THREAD) {
     int rc = grid_for(ctx, w2a::step_thread_kernel<ADT>, 128, 0, 128, a.n, &grid);
@@ -192,6 +198,8 @@ int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int varia
 int step_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const void* action, int action_dtype,
                 const uint2* st_static, uint2* st_mut, float* obs, float* reward,
                 uint8_t* terminated, int32_t* remaining, uint8_t* at_budget, int variant) {
+  const bool local = (variant & W2A_STEP_LOCAL) != 0;  // tuning hint, see w2a.h
+  variant &= ~W2A_STEP_LOCAL;
   if (variant == W2A_STEP_AUTO) variant = W2A_STEP_COOP;  // faster than THREAD at every batch size, n = 1 included
   if (variant != W2A_STEP_THREAD && variant != W2A_STEP_COOP && variant != W2A_STEP_TABLE)
     return fail(ctx, W2A_E_INVALID, "w2a_step: unknown variant %d", variant);
@@ -212,9 +220,9 @@ int step_planes(w2a_ctx* ctx, cudaStream_t st, int64_t n, const void* action, in
   // kept L2-resident between steps (evict_last), beyond that they stream
   a.keep_state = n <= ctx->keep_state_max_envs ? 1 : 0;
   switch (action_dtype) {
-    case W2A_ACT_U8: return launch_step<0>(ctx, st, a, variant);
-    case W2A_ACT_I32: return launch_step<1>(ctx, st, a, variant);
-    case W2A_ACT_I64: return launch_step<2>(ctx, st, a, variant);
+    case W2A_ACT_U8: return launch_step<0>(ctx, st, a, variant, local);
+    case W2A_ACT_I32: return launch_step<1>(ctx, st, a, variant, local);
+    case W2A_ACT_I64: return launch_step<2>(ctx, st, a, variant, local);
     default: return fail(ctx, W2A_E_INVALID, "w2a_step: unknown action_dtype %d", action_dtype);
   }
 }
@@ -296,6 +304,7 @@ int w2a_create(int device, w2a_ctx** out) {
   const char* pdl_env = std::getenv("W2A_PDL");  // tuning switch: W2A_PDL=0 launches the step kernels fully serialised
   ctx->pdl = !(pdl_env && pdl_env[0] == '0');
   if (const char* ks = std::getenv("W2A_KEEP_STATE_MAX")) ctx->keep_state_max_envs = std::atoll(ks);
+  if (const char* r1 = std::getenv("W2A_TABLE_ROWS1_MAX")) ctx->table_rows1_max_envs = std::atoll(r1);
   if (const char* sm = std::getenv("W2A_SMALL_TABLE")) ctx->small_table_groups_per_sm = std::atoi(sm);
   if (const char* pp = std::getenv("W2A_PDL_POLICY")) ctx->pdl_policy = std::atoi(pp) != 0;
   if (const char* hc = std::getenv("W2A_HOST_CHUNK")) g_host_chunk = std::max<int64_t>(1024, std::atoll(hc));
@@ -579,6 +588,19 @@ int w2a_reset_host(w2a_ctx* ctx, const int32_t* loc, const int32_t* year, const 
       h->n_noncanon += static_cast<int64_t>(non) - static_cast<int64_t>(h->noncanon[static_cast<size_t>(i)]);
       h->noncanon[static_cast<size_t>(i)] = non;
     }
+    // env slots in table order? (a full reset decides; a masked one scatters fresh episodes over them)
+    if (mask) {
+      h->local = false;
+    } else {
+      bool sorted = true;
+      for (int64_t i = 1; i < n && sorted; ++i) {
+        if (loc[i] != loc[i - 1]) sorted = loc[i] > loc[i - 1];
+        else if (coef_col[i] != coef_col[i - 1]) sorted = coef_col[i] > coef_col[i - 1];
+        else if (coef_idx[i] != coef_idx[i - 1]) sorted = coef_idx[i] > coef_idx[i - 1];
+        else sorted = year[i] >= year[i - 1];
+      }
+      h->local = sorted;
+    }
   }
   int ci = 0;
   const int64_t chunk = host_chunk(n);
@@ -623,7 +645,7 @@ int w2a_step_host(w2a_ctx* ctx, const uint8_t* action, float* obs, float* reward
   uint2* smut = plane_mut(h->state, n);
   // one kernel variant for the whole batch, so that chunking never changes a result bit: the tabulated
   // logits when every env steps on its own county's column and the tables exist, else the cooperative kernel
-  const int variant = (ctx->tb.z32_all && h->n_noncanon == 0) ? W2A_STEP_TABLE : W2A_STEP_COOP;
+  const int variant = (ctx->tb.z32_all && h->n_noncanon == 0) ? (W2A_STEP_TABLE | (h->local ? W2A_STEP_LOCAL : 0)) : W2A_STEP_COOP;
   if (h->packed) {
     const size_t un = static_cast<size_t>(n), obs_b = un * W2A_OBS_DIM * sizeof(float);
     cudaStream_t st = h->streams[0];
@@ -878,7 +900,7 @@ int w2a_step_mlp(w2a_ctx* ctx, void* stream, int64_t n, const uint8_t* action, v
   if (rc) return rc;
   W2A_CUDA(ctx, cudaSetDevice(ctx->device));
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (variant != W2A_STEP_TABLE || !ctx->tb.z32_all) {
+  if ((variant & ~W2A_STEP_LOCAL) != W2A_STEP_TABLE || !ctx->tb.z32_all) {
     // no tables (or another variant asked for): the same result from two launches, and the return sum from a third
     rc = step_planes(ctx, st, n, action, W2A_ACT_U8, plane_static(state), plane_mut(state, n), obs, reward, terminated, remaining,
                      at_budget, variant);

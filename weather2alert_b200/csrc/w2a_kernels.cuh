@@ -757,8 +757,11 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 #endif               // 2 sector gather from entry 0, 4 row gather from row 0, 8 no reward / flag outputs, 16 sectors of day 0
                      // whatever the day (the slice stays in L2), 64 / 128 the sector gather with 4 / 1 distinct lines per load
 
-// ROWS = rounds of row gathers in flight per warp: W2A_TABLE_ROWS for the bandwidth-bound sizes; 8 (every gather of the
-// group issued before anything waits) for env sets of a few groups per SM, where a step is a chain of memory latencies.
+// ROWS = rounds of row gathers in flight per warp.  2 (W2A_TABLE_ROWS) where the step is bandwidth-bound: env slots with
+// locality, or more than ~3M envs; 1 for up to ~3M envs without locality, where the cold sector gather sets the pace and a
+// second row round in flight only gets in its way (B200, 2^20 interleaved envs: 33.3 vs 34.5 us; sorted: 29.7 vs 28.5;
+// 2^23: 248 vs 238); 8 (every gather of the group issued before anything waits) for env sets of a few groups per SM,
+// where a step is a chain of memory latencies.
 // `post` hooks a consumer of the fresh observations into the kernel (w2a_policy.cuh: the MLP policy that picks the next
 // action from the rows while they are still in shared memory); StepNoPost is the plain step.
 struct StepNoPost {
@@ -963,7 +966,7 @@ __device__ __forceinline__ void step_table_body(const StepArgs& p, Post& post) {
 }
 
 template <int ADT, int ROWS = W2A_TABLE_ROWS>
-__global__ void __launch_bounds__(32 * kTableWarps, ROWS == W2A_TABLE_ROWS ? W2A_TABLE_MINBLOCKS : 4) step_table_kernel(const StepArgs p) {
+__global__ void __launch_bounds__(32 * kTableWarps, ROWS <= 2 ? W2A_TABLE_MINBLOCKS : 4) step_table_kernel(const StepArgs p) {
   StepNoPost post;
   step_table_body<ADT, ROWS>(p, post);
 }

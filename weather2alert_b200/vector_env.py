@@ -148,6 +148,7 @@ class HeatAlertVectorEnv(VectorEnv):
         self._atb = torch.zeros(n, dtype=torch.bool, device=dev)
         self._bound = {}
         self._canonical = False  # every env's coefficient column is its own county (set by each draw)
+        self._slots_sorted = False  # the env slots are in table order (last full reset was locality-sorted): a hint for the step
         # rollout statistics a la AlertLoggingCallback (callbacks.py:63-74); `stats.reduce()` all-reduces them
         self.stats = None
         if track_stats:
@@ -324,6 +325,9 @@ class HeatAlertVectorEnv(VectorEnv):
     def _reset_subset(self, mask):
         s = self._draw(sort=mask is None)
         self._idx = s
+        o = self._reset_opts
+        self._slots_sorted = bool(mask is None and self.sort_episodes and "index_streams" not in o
+                                  and not o.get("reference_rng", False))
         self.core.reset(self._state, self._obs, s["loc"], s["year"], s["coef_col"], s["coef_idx"],
                         budget=s.get("budget"), mask=mask, remaining=self._rem)
         if mask is None:
@@ -356,7 +360,8 @@ class HeatAlertVectorEnv(VectorEnv):
         for building the table (`HeatAlertCore.choose_variant`)."""
         if self.step_variant != _lib.STEP_AUTO:
             return self.step_variant
-        return self.core.choose_variant(self.num_envs, canonical=self._canonical)
+        v = self.core.choose_variant(self.num_envs, canonical=self._canonical)
+        return v | _lib.STEP_LOCAL if (v == _lib.STEP_TABLE and self._slots_sorted) else v
 
     def step(self, actions: torch.Tensor):
         if self._next_term is None:
@@ -521,7 +526,7 @@ class HeatAlertVectorEnv(VectorEnv):
         opts = {k: v for k, v in self._reset_opts.items()}
         sd = {"state": self._state.clone(), "obs": self._obs.clone(), "rem": self._rem.clone(), "atb": self._atb.clone(),
               "step_no": self._step_no, "term_at": None if self._term_at is None else self._term_at.clone(),
-              "next_term": self._next_term, "canonical": self._canonical, "reset_opts": opts,
+              "next_term": self._next_term, "canonical": self._canonical, "slots_sorted": self._slots_sorted, "reset_opts": opts,
               "ep_loc": self._ep_loc.clone(), "ep_year": self._ep_year.clone(), "coef_col": self._coef_col.clone(),
               "list_idx": self._list_idx.clone(),
               "gen": self._gen.get_state(), "host_rng": self._host_rng.bit_generator.state}
@@ -538,6 +543,7 @@ class HeatAlertVectorEnv(VectorEnv):
         self._term_at = None if sd["term_at"] is None else sd["term_at"].clone()
         self._next_term = sd["next_term"]
         self._canonical = bool(sd["canonical"])
+        self._slots_sorted = bool(sd.get("slots_sorted", False))
         self._reset_opts = dict(sd["reset_opts"])
         self._ep_loc, self._ep_year = sd["ep_loc"].clone(), sd["ep_year"].clone()
         self._coef_col, self._list_idx = sd["coef_col"].clone(), sd["list_idx"].clone()
