@@ -163,6 +163,10 @@ int launch_step(w2a_ctx* ctx, cudaStream_t st, const w2a::StepArgs& a, int varia
       int rc = grid_for(ctx, w2a::step_table_kernel<ADT, 1>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);
       if (rc) return rc;
       W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT, 1>, grid, kBlock, w2a::kTableSmemBytes, st, ctx->pdl, a));
+    } else if (local && a.keep_state) {  // table order and the state L2-resident: no row gather before the logits are done
+      int rc = grid_for(ctx, w2a::step_table_kernel<ADT, 2, true>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);
+      if (rc) return rc;
+      W2A_CUDA(ctx, launch_kernel(w2a::step_table_kernel<ADT, 2, true>, grid, kBlock, w2a::kTableSmemBytes, st, ctx->pdl, a));
     } else {
       int rc = grid_for(ctx, w2a::step_table_kernel<ADT, 2>, kBlock, w2a::kTableSmemBytes, kBlock, a.n, &grid);
       if (rc) return rc;

@@ -762,13 +762,16 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
 // second row round in flight only gets in its way (B200, 2^20 interleaved envs: 33.3 vs 34.5 us; sorted: 29.7 vs 28.5;
 // 2^23: 248 vs 238); 8 (every gather of the group issued before anything waits) for env sets of a few groups per SM,
 // where a step is a chain of memory latencies.
+// LATE = no row gather is issued before the group's logits and rewards are done (instead of the first ROWS rounds right
+// behind the sector): for slots in table order whose state stays in L2 (sorted 2^20 envs: 27.2 vs 28.5 us; no difference
+// without locality; slower when the state streams from HBM: 2^23 envs 249 vs 238).
 // `post` hooks a consumer of the fresh observations into the kernel (w2a_policy.cuh: the MLP policy that picks the next
 // action from the rows while they are still in shared memory); StepNoPost is the plain step.
 struct StepNoPost {
   __device__ __forceinline__ void reward(int, float) const {}
   __device__ __forceinline__ void group(const float*, int, int) const {}
 };
-template <int ADT, int ROWS, typename Post>
+template <int ADT, int ROWS, bool LATE, typename Post>
 __device__ __forceinline__ void step_table_body(const StepArgs& p, Post& post) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const stage = reinterpret_cast<TableScratchWarp*>(smem_raw)[threadIdx.x >> 5].obs;
@@ -869,7 +872,7 @@ __device__ __forceinline__ void step_table_body(const StepArgs& p, Post& post) {
         }
       }
     };
-    load_rows(0);
+    if (!LATE) load_rows(0);
 #if W2A_STATE_KEEP
     if (valid && p.keep_state) st_keep_u2(p.st_mut + e, mv, keep_state);
     else
@@ -937,7 +940,7 @@ __device__ __forceinline__ void step_table_body(const StepArgs& p, Post& post) {
     }
 #pragma unroll
     for (int first = 0; first < 8; first += ROWS) {
-      if (first > 0) load_rows(first);
+      if (first > 0 || LATE) load_rows(first);
       stage_rows(first);
     }
     __syncwarp();
@@ -965,10 +968,10 @@ __device__ __forceinline__ void step_table_body(const StepArgs& p, Post& post) {
   if (bulk_pending && lane == 0) bulk_store_wait_all();
 }
 
-template <int ADT, int ROWS = W2A_TABLE_ROWS>
-__global__ void __launch_bounds__(32 * kTableWarps, ROWS <= 2 ? W2A_TABLE_MINBLOCKS : 4) step_table_kernel(const StepArgs p) {
+template <int ADT, int ROWS = W2A_TABLE_ROWS, bool LATE = false>
+__global__ void __launch_bounds__(32 * kTableWarps, ROWS <= 4 ? W2A_TABLE_MINBLOCKS : 4) step_table_kernel(const StepArgs p) {
   StepNoPost post;
-  step_table_body<ADT, ROWS>(p, post);
+  step_table_body<ADT, ROWS, LATE>(p, post);
 }
 
 // =========================================================================================

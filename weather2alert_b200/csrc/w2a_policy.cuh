@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(32 * kTableWarps, W2A_STEP_MLP_MINBLOCKS) step
   pdl_wait();
   mlp_load_weights<NT>(m, post.w1s, post.w2f);
   __syncthreads();
-  step_table_body<ADT, W2A_STEP_MLP_ROWS>(p, post);
+  step_table_body<ADT, W2A_STEP_MLP_ROWS, false>(p, post);
 }
 
 }  // namespace w2a
