@@ -76,7 +76,7 @@ struct w2a_ctx {
   void* table_scratch = nullptr;  // z32_all | zt_all | x32 | pt, owned by the context (w2a_precompute_logits)
   std::vector<int32_t> col_to_loc_host;  // host copy of the county map (canonical check of the *_host resets)
   int64_t keep_state_max_envs = 3 << 19;  // W2A_KEEP_STATE_MAX overrides (0 = never)
-  int64_t table_rows1_max_envs = 3 << 20;  // TABLE step without the locality hint: up to this many envs one row round in flight (W2A_TABLE_ROWS1_MAX)
+  int64_t table_rows1_max_envs = 5 << 20;  // TABLE step without the locality hint: up to this many envs one row round in flight (W2A_TABLE_ROWS1_MAX)
   int small_table_groups_per_sm = 16;  // TABLE step: env sets of up to this many 32-env groups per SM take the one-warp-per-CTA instance (W2A_SMALL_TABLE overrides, 0 = never)
   bool pdl_policy = false;        // the policy and step + policy kernels are launched serialised: as programmatic dependents they run
                                   // 1-10 us per iteration SLOWER in the graphed loop (B200, 2^20 envs; W2A_PDL_POLICY=1 to compare)

@@ -758,10 +758,12 @@ constexpr int kTableSmemBytes = kTableWarps * static_cast<int>(sizeof(TableScrat
                      // whatever the day (the slice stays in L2), 64 / 128 the sector gather with 4 / 1 distinct lines per load
 
 // ROWS = rounds of row gathers in flight per warp.  2 (W2A_TABLE_ROWS) where the step is bandwidth-bound: env slots with
-// locality, or more than ~3M envs; 1 for up to ~3M envs without locality, where the cold sector gather sets the pace and a
+// locality, or more than ~5M envs; 1 for up to ~5M envs without locality, where the cold sector gather sets the pace and a
 // second row round in flight only gets in its way (B200, 2^20 interleaved envs: 33.3 vs 34.5 us; sorted: 29.7 vs 28.5;
 // 2^23: 248 vs 238); 8 (every gather of the group issued before anything waits) for env sets of a few groups per SM,
 // where a step is a chain of memory latencies.
+// The one-round instance runs 7 CTAs per SM (72 registers) instead of 8: 33.0 vs 33.3 us at 2^20 envs, 17.7 vs 19.4 at 2^19,
+// 6.4 vs 6.8 at 2^17 -- fewer warps asking at once, again; the two-round instances lose 3 % with 7.
 // LATE = no row gather is issued before the group's logits and rewards are done (instead of the first ROWS rounds right
 // behind the sector): for slots in table order whose state stays in L2 (sorted 2^20 envs: 27.2 vs 28.5 us; no difference
 // without locality; slower when the state streams from HBM: 2^23 envs 249 vs 238).
@@ -969,7 +971,8 @@ __device__ __forceinline__ void step_table_body(const StepArgs& p, Post& post) {
 }
 
 template <int ADT, int ROWS = W2A_TABLE_ROWS, bool LATE = false>
-__global__ void __launch_bounds__(32 * kTableWarps, ROWS <= 4 ? W2A_TABLE_MINBLOCKS : 4) step_table_kernel(const StepArgs p) {
+__global__ void __launch_bounds__(32 * kTableWarps, ROWS == 1 ? W2A_TABLE_MINBLOCKS - 1 : ROWS <= 4 ? W2A_TABLE_MINBLOCKS : 4)
+    step_table_kernel(const StepArgs p) {
   StepNoPost post;
   step_table_body<ADT, ROWS, LATE>(p, post);
 }
