@@ -163,6 +163,16 @@ def test_auto_variant_rule_above_the_abi():
     assert pick(HeatAlertCore.TABLE_MIN_ENVS, True) == _lib.STEP_TABLE
     assert pick(HeatAlertCore.TABLE_MIN_ENVS - 1, True) == _lib.STEP_AUTO
     assert _lib.POLICY_LEN == 30 and _lib.STEP_TABLE == 3
+    # the Python constants are the header's
+    import re
+
+    hdr = open(os.path.join(REPO, "include", "w2a.h")).read()
+    defs = {k: int(v, 0) for k, v in re.findall(r"#define (W2A_[A-Z0-9_]+) (0x[0-9a-fA-F]+|-?\d+)\b", hdr)}
+    for name, val in (("W2A_STEP_AUTO", _lib.STEP_AUTO), ("W2A_STEP_THREAD", _lib.STEP_THREAD), ("W2A_STEP_COOP", _lib.STEP_COOP),
+                      ("W2A_STEP_TABLE", _lib.STEP_TABLE), ("W2A_STEP_LOCAL", _lib.STEP_LOCAL), ("W2A_OBS_DIM", _lib.OBS_DIM),
+                      ("W2A_POLICY_LEN", _lib.POLICY_LEN)):
+        assert defs[name] == val, name
+    assert _lib.STEP_LOCAL & 0xFF == 0  # a flag above the variant numbers
 
 
 def test_no_product_module_imports_the_oracle():
